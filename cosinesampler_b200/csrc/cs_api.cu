@@ -1,0 +1,229 @@
+// cs_api.cu -- extern "C" boundary of libcosine_sampler_b200.so
+// (see include/cosine_sampler_b200.h for the contract and the reference
+// interfaces each entry point replaces) plus the layout-staging kernels.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cosine_sampler_b200.h"
+#include "cs_engine.cuh"
+
+namespace cs {
+cudaError_t launch_stage_2d(int vec, int stage, bool has_u, bool has_x2, const StageParams& p, cudaStream_t s);
+cudaError_t launch_stage_3d(int vec, int stage, bool has_u, bool has_x2, const StageParams& p, cudaStream_t s);
+}  // namespace cs
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int gcd8(int v) {  // largest power of two <= 8 dividing v
+    int l = 1;
+    while (l < 8 && v % (l * 2) == 0) l *= 2;
+    return l;
+}
+
+// Validate the problem and fill the geometry part of StageParams.
+int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const float* offset) {
+    if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
+    if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
+    if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
+    if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
+    if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
+    if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
+    if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
+    if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
+    if (pb->field_layout < 0 || pb->field_layout > 1) return fail(CS_EINVAL, "bad field_layout %d", pb->field_layout);
+    if (pb->lanes != 0 && pb->lanes != 1 && pb->lanes != 2 && pb->lanes != 4 && pb->lanes != 8)
+        return fail(CS_EINVAL, "lanes must be 0,1,2,4 or 8");
+    if (!grid || !offset) return fail(CS_EINVAL, "grid/offset pointer is NULL");
+    const long long T = (long long)pb->D * pb->H * pb->W;
+    if (T * (long long)pb->C >= (1ll << 31))
+        return fail(CS_EUNSUPPORTED, "a cell has %lld elements; the per-cell index is 32-bit", T * pb->C);
+    memset(&p, 0, sizeof(p));
+    p.N = pb->N; p.C = pb->C; p.P = pb->P;
+    p.size[0] = pb->W; p.size[1] = pb->H; p.size[2] = pb->D;
+    p.tstride[0] = 1; p.tstride[1] = pb->W; p.tstride[2] = pb->W * pb->H;
+    p.cell_stride = T * pb->C;
+    if (pb->field_layout == CS_LAYOUT_CHANNEL_LAST) { p.texel_stride = pb->C; p.chan_stride = 1; }
+    else { p.texel_stride = 1; p.chan_stride = (int)T; }
+    p.grid = grid; p.grid_sn = pb->grid_stride_n; p.offset = offset;
+    p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
+    p.multicell = pb->multicell; p.index_mode = pb->index_mode;
+    return 0;
+}
+
+bool stream_vec_ok(const cs_stream& s) {
+    return s.ptr == nullptr || (aligned16(s.ptr) && s.stride_n % 4 == 0 && s.stride_c % 4 == 0);
+}
+
+int run(const cs_problem* pb, cs::StageParams& p, int stage, bool has_u, bool has_x2, void* stream) {
+    if (p.N == 0 || p.C == 0 || p.P == 0) return 0;   // empty problem: nothing to launch (cu2d:904)
+    // field vector width
+    bool vec4 = (pb->field_layout == CS_LAYOUT_CHANNEL_LAST) && (p.C % 4 == 0) &&
+                aligned16(p.V) && aligned16(p.U) && aligned16(p.acc);
+    const int vec = vec4 ? 4 : 1;
+    int lanes = pb->lanes ? pb->lanes : gcd8(p.C / vec);
+    p.lshift = (lanes == 1) ? 0 : (lanes == 2) ? 1 : (lanes == 4) ? 2 : 3;
+    const int pts = 128 >> p.lshift;
+    p.num_ptiles = (p.P + pts - 1) / pts;
+    // stream vector width
+    p.svec4 = (p.P % 4 == 0) && aligned16(p.x1) && aligned16(p.x2) && aligned16(p.y) &&
+              p.x1_sn % 4 == 0 && p.x1_sc % 4 == 0 && p.x2_sn % 4 == 0 && p.x2_sc % 4 == 0;
+    cudaError_t e = (pb->dim == 2)
+        ? cs::launch_stage_2d(vec, stage, has_u, has_x2, p, (cudaStream_t)stream)
+        : cs::launch_stage_3d(vec, stage, has_u, has_x2, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stage kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Layout staging: [N, C, T] <-> [N, T, C]
+// A block moves a 32-texel x 32-channel tile through shared memory so that both
+// the T-contiguous side and the C-contiguous side are accessed in runs.
+// ---------------------------------------------------------------------------
+template <bool TO_CL, bool ACCUM>
+__global__ void __launch_bounds__(256) cs_layout_kernel(const float* __restrict__ src,
+                                                        float* __restrict__ dst, int C, long long T) {
+    __shared__ float tile[32][33];          // [channel][texel]
+    const int n = blockIdx.z;
+    const long long t0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int ct = min(32, C - c0);
+    const float* s = src + (long long)n * C * T;
+    float* d = dst + (long long)n * C * T;
+    if (TO_CL) {
+        // read [c][t] rows (t contiguous)
+        for (int c = ty; c < ct; c += 8)
+            if (t0 + tx < T) tile[c][tx] = s[(long long)(c0 + c) * T + t0 + tx];
+        __syncthreads();
+        // write [t][c]: linear over the (texel, channel) pairs of the tile
+        for (int idx = threadIdx.x; idx < 32 * ct; idx += 256) {
+            const int t = idx / ct, c = idx - t * ct;
+            if (t0 + t < T) d[(t0 + t) * C + c0 + c] = tile[c][t];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < 32 * ct; idx += 256) {
+            const int t = idx / ct, c = idx - t * ct;
+            if (t0 + t < T) tile[c][t] = s[(t0 + t) * C + c0 + c];
+        }
+        __syncthreads();
+        for (int c = ty; c < ct; c += 8) {
+            if (t0 + tx < T) {
+                float* o = d + (long long)(c0 + c) * T + t0 + tx;
+                if (ACCUM) *o += tile[c][tx]; else *o = tile[c][tx];
+            }
+        }
+    }
+}
+
+int layout_launch(const float* src, float* dst, int N, int C, long long T, int mode, void* stream) {
+    if (N < 0 || C < 0 || T < 0) return fail(CS_EINVAL, "negative size");
+    if (N == 0 || C == 0 || T == 0) return 0;
+    if (!src || !dst) return fail(CS_EINVAL, "NULL buffer");
+    const long long bx = (T + 31) / 32;
+    if (bx > 0x7fffffffll || N > 65535 || (C + 31) / 32 > 65535)
+        return fail(CS_EUNSUPPORTED, "layout kernel grid too large");
+    dim3 grid((unsigned)bx, (unsigned)((C + 31) / 32), (unsigned)N);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == 0) cs_layout_kernel<true, false><<<grid, 256, 0, s>>>(src, dst, C, T);
+    else if (mode == 1) cs_layout_kernel<false, false><<<grid, 256, 0, s>>>(src, dst, C, T);
+    else cs_layout_kernel<false, true><<<grid, 256, 0, s>>>(src, dst, C, T);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "layout kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_version(void) { return CS_VERSION; }
+const char* cs_last_error(void) { return g_err; }
+uint64_t cs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int cs_forward(const cs_problem* pb, const float* input, const float* grid, const float* offset,
+               float* out, void* stream) {
+    cs::StageParams p;
+    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (!input || !out) return fail(CS_EINVAL, "cs_forward: input/out is NULL");
+    p.V = input; p.y = out;
+    return run(pb, p, cs::ST_F, false, false, stream);
+}
+
+int cs_backward(const cs_problem* pb, cs_stream gOut, const float* input, const float* grid,
+                const float* offset, float* gInput, float* gGrid, void* stream) {
+    cs::StageParams p;
+    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (!gOut.ptr) return fail(CS_EINVAL, "cs_backward: gOut is NULL");
+    if (gGrid && !input) return fail(CS_EINVAL, "cs_backward: gGrid needs input");
+    if (!gInput && !gGrid) return 0;
+    p.V = input; p.acc = gInput; p.ggrid = gGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    return run(pb, p, cs::ST_B, false, false, stream);
+}
+
+int cs_backward_backward(const cs_problem* pb, const float* gOutInput, const float* gOutGrid,
+                         const float* input, const float* grid, cs_stream gOut, const float* offset,
+                         float* gInput, float* gGrid, float* ggOut, void* stream) {
+    cs::StageParams p;
+    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (!gOut.ptr || !gOutGrid) return fail(CS_EINVAL, "cs_backward_backward: gOut/gOutGrid is NULL");
+    if ((gGrid || ggOut) && !input) return fail(CS_EINVAL, "cs_backward_backward: gGrid/ggOut need input");
+    if (!gInput && !gGrid && !ggOut) return 0;
+    // gOutInput only feeds ggOut (2D and 3D) and gGrid (3D): skip its gather when neither is wanted
+    const bool has_u = gOutInput && (ggOut || (gGrid && pb->dim == 3));
+    p.V = input; p.U = has_u ? gOutInput : nullptr; p.acc = gInput; p.ggrid = gGrid; p.y = ggOut;
+    p.gog = gOutGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    return run(pb, p, cs::ST_BB, has_u, false, stream);
+}
+
+int cs_backward_backward_backward(const cs_problem* pb, const float* input, const float* grid,
+                                  cs_stream gOut, const float* gOutGrid, const float* gOutgGrid,
+                                  cs_stream gOutggOut, const float* offset, float* gInput,
+                                  float* ggOut, void* stream) {
+    cs::StageParams p;
+    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (!gOut.ptr || !gOutGrid || !gOutgGrid)
+        return fail(CS_EINVAL, "cs_backward_backward_backward: gOut/gOutGrid/gOutgGrid is NULL");
+    if (ggOut && !input) return fail(CS_EINVAL, "cs_backward_backward_backward: ggOut needs input");
+    if (!gInput && !ggOut) return 0;
+    const bool has_x2 = gOutggOut.ptr && gInput;
+    p.V = input; p.acc = gInput; p.y = ggOut;
+    p.gog = gOutGrid; p.gogg = gOutgGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (has_x2) { p.x2 = gOutggOut.ptr; p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
+    return run(pb, p, cs::ST_BBB, false, has_x2, stream);
+}
+
+int cs_to_channel_last(const float* src, float* dst, int32_t N, int32_t C, int64_t T, void* stream) {
+    return layout_launch(src, dst, N, C, T, 0, stream);
+}
+
+int cs_from_channel_last(const float* src, float* dst, int32_t N, int32_t C, int64_t T,
+                         int32_t accumulate, void* stream) {
+    return layout_launch(src, dst, N, C, T, accumulate ? 2 : 1, stream);
+}
+
+}  // extern "C"

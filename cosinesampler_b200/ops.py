@@ -1,0 +1,344 @@
+"""Stage-level operators on torch tensors: the host-side mirror of the
+reference's native surface (pybind `_cosine_2d` / `_cosine_3d`:
+`forward`, `backward`, `backward_backward`, `backward_backward_backward`,
+`cosine_sampler_2d.cpp:47-135`, `cosine_sampler_3d.cpp:50-138`), same argument
+order and meaning, dispatching to the C ABI in libcosine_sampler_b200.so.
+
+torch is used here for device memory (outputs come from the caching
+allocator on the current stream) and nothing else; every kernel is ours.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+_INDEX_MODE = _lib.INDEX_FUSED if os.environ.get("COSINE_SAMPLER_INDEX_MODE", "").lower() == "fused" \
+    else _lib.INDEX_SEPARATE
+_LANES = int(os.environ.get("COSINE_SAMPLER_LANES", "0"))
+
+
+def set_index_mode(mode):
+    """'separate' (default; rounds like test/grid_sampler.py:37-38) or 'fused'
+    (one fma, like the reference CUDA build with --use_fast_math).  SURVEY 7.1."""
+    global _INDEX_MODE
+    _INDEX_MODE = {"separate": _lib.INDEX_SEPARATE, "fused": _lib.INDEX_FUSED}[mode]
+
+
+def get_index_mode():
+    return "fused" if _INDEX_MODE == _lib.INDEX_FUSED else "separate"
+
+
+def set_lanes(lanes):
+    """0 = automatic; 1/2/4/8 lanes per point quad (1 = whole channel loop in one thread)."""
+    global _LANES
+    assert lanes in (0, 1, 2, 4, 8)
+    _LANES = lanes
+
+
+# ---------------------------------------------------------------------------
+# argument checks (the reference's CHECK_INPUT, cosine_sampler_2d.cpp:4-6)
+# ---------------------------------------------------------------------------
+def _check(t, name, contiguous=True):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (the reference kernels are fp32-only), got %s"
+                           % (name, t.dtype))
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+
+
+def _geometry(input, grid):
+    dim = grid.shape[-1]
+    if dim not in (2, 3) or input.dim() != dim + 2 or grid.dim() != dim + 2:
+        raise RuntimeError("expected input [N,C,(D,)H,W] and grid [N,(Do,)Ho,Wo,dim]; got %s and %s"
+                           % (tuple(input.shape), tuple(grid.shape)))
+    if grid.shape[0] != input.shape[0]:
+        raise RuntimeError("grid batch (%d) must equal input batch (%d)" % (grid.shape[0], input.shape[0]))
+    N, C = input.shape[0], input.shape[1]
+    if dim == 2:
+        D, (H, W) = 1, input.shape[2:]
+    else:
+        D, H, W = input.shape[2:]
+    P = 1
+    for s in grid.shape[1:-1]:
+        P *= s
+    return dim, N, C, D, H, W, P
+
+
+def _grid_view(grid, name="grid"):
+    """grid must be contiguous, or expanded along the cell axis (stride 0)."""
+    if not grid.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if grid.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+    if grid.is_contiguous():
+        n_stride = grid[0].numel() if grid.shape[0] > 0 else 0
+        return grid, n_stride
+    if grid.shape[0] > 0 and grid.stride(0) == 0 and grid[0].is_contiguous():
+        return grid, 0
+    raise RuntimeError("%s must be contiguous" % name)
+
+
+def _as_stream(t, P, name):
+    """View a [N,C,*spatial] tensor as a strided [N,C,P] stream without copying when
+    its point axis is dense (PIXEL hands us gOut expanded over N); else copy."""
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+    ok = True
+    expect = 1
+    for d in range(t.dim() - 1, 1, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            ok = False
+            break
+        expect *= t.shape[d]
+    if not ok or t.stride(0) < 0 or t.stride(1) < 0:
+        t = t.contiguous()
+    return t, _lib.Stream3(t.data_ptr(), t.stride(0), t.stride(1))
+
+
+_NULL_STREAM = None
+
+
+def _null_stream():
+    return _lib.Stream3(None, 0, 0)
+
+
+class Staged:
+    """Channel-last copy [N, T, C] of a grid-shaped field, valid for the field as it
+    was when staged (identified by storage pointer and version counter)."""
+    __slots__ = ("ptr", "version", "shape", "cl")
+
+    def __init__(self, t, cl):
+        self.ptr, self.version, self.shape, self.cl = t.data_ptr(), t._version, tuple(t.shape), cl
+
+    def matches(self, t):
+        return (t.data_ptr() == self.ptr and t._version == self.version
+                and tuple(t.shape) == self.shape)
+
+
+def _cur_stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """cheap device guard (cosine_sampler_2d.cpp:53): only switches when needed"""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def uses_channel_last(C):
+    return C > 0 and C % 4 == 0
+
+
+def to_channel_last(field):
+    """[N,C,*S] -> [N,T,C] copy through cs_to_channel_last."""
+    N, C = field.shape[:2]
+    T = field[0, 0].numel() if N > 0 and C > 0 else 0
+    cl = torch.empty((N, T, C), dtype=field.dtype, device=field.device)
+    with _on_device(field.device):
+        rc = _lib.load().cs_to_channel_last(field.data_ptr(), cl.data_ptr(), N, C, T,
+                                            _cur_stream(field.device))
+    _lib.check(rc, "cs_to_channel_last")
+    return cl
+
+
+def from_channel_last(cl, shape, out=None, accumulate=False):
+    """[N,T,C] -> [N,C,*S]."""
+    N, C = shape[:2]
+    T = cl.shape[1]
+    if out is None:
+        out = torch.empty(shape, dtype=cl.dtype, device=cl.device)
+        accumulate = False
+    with _on_device(cl.device):
+        rc = _lib.load().cs_from_channel_last(cl.data_ptr(), out.data_ptr(), N, C, T,
+                                              1 if accumulate else 0, _cur_stream(cl.device))
+    _lib.check(rc, "cs_from_channel_last")
+    return out
+
+
+def stage(field):
+    """Stage a field for vector gathers, or None when its channel count rules that out."""
+    if not uses_channel_last(field.shape[1]):
+        return None
+    return Staged(field, to_channel_last(field))
+
+
+def _field(input, staged):
+    """-> (pointer tensor, layout) for the gather side."""
+    if staged is not None and staged.matches(input):
+        return staged.cl, _lib.LAYOUT_CHANNEL_LAST
+    if uses_channel_last(input.shape[1]):
+        return to_channel_last(input), _lib.LAYOUT_CHANNEL_LAST
+    return input, _lib.LAYOUT_CHANNEL_FIRST
+
+
+def _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn):
+    pb = _lib.Problem()
+    pb.dim, pb.N, pb.C, pb.D, pb.H, pb.W, pb.P = dim, N, C, D, H, W, P
+    pb.padding_mode = int(padding_mode)
+    pb.align_corners = 1 if align_corners else 0
+    pb.kernel = int(kernel)
+    pb.multicell = 1 if multicell else 0
+    pb.index_mode = _INDEX_MODE
+    pb.field_layout = layout
+    pb.grid_stride_n = grid_sn
+    pb.lanes = _LANES
+    return pb
+
+
+def _new_accumulator(input, layout):
+    N, C = input.shape[:2]
+    if layout == _lib.LAYOUT_CHANNEL_LAST:
+        T = input[0, 0].numel() if N > 0 and C > 0 else 0
+        return torch.zeros((N, T, C), dtype=input.dtype, device=input.device)
+    return torch.zeros_like(input, memory_format=torch.contiguous_format)
+
+
+def _finish_accumulator(acc, input, layout):
+    if layout == _lib.LAYOUT_CHANNEL_LAST:
+        return from_channel_last(acc, tuple(input.shape))
+    return acc
+
+
+# ---------------------------------------------------------------------------
+# the four entry points
+# ---------------------------------------------------------------------------
+def forward(input, grid, offset, padding_mode, align_corners, kernel, multicell, staged=None):
+    """`_cosine_Xd.forward` (cpp2d:47-62): returns out [N,C,*grid.shape[1:-1]]."""
+    _check(input, "input")
+    grid, grid_sn = _grid_view(grid)
+    _check(offset, "offset")
+    dim, N, C, D, H, W, P = _geometry(input, grid)
+    field, layout = _field(input, staged)
+    out = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device)
+    pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
+    with _on_device(input.device):
+        rc = _lib.load().cs_forward(pb, field.data_ptr(), grid.data_ptr(), offset.data_ptr(),
+                                    out.data_ptr(), _cur_stream(input.device))
+    _lib.check(rc, "cs_forward")
+    return out
+
+
+def backward(gOut, input, grid, offset, padding_mode, align_corners, input_requires_grad, kernel,
+             multicell, staged=None, want_grid=True):
+    """`_cosine_Xd.backward` (cpp2d:64-85): returns (gInput or None, gGrid).
+    want_grid=False additionally elides gGrid (returns None for it)."""
+    _check(input, "input")
+    grid, grid_sn = _grid_view(grid)
+    _check(offset, "offset")
+    dim, N, C, D, H, W, P = _geometry(input, grid)
+    gOut, gs = _as_stream(gOut, P, "grad_output")
+    if want_grid:
+        field, layout = _field(input, staged)
+    else:
+        field = None
+        layout = _lib.LAYOUT_CHANNEL_LAST if uses_channel_last(C) else _lib.LAYOUT_CHANNEL_FIRST
+    acc = _new_accumulator(input, layout) if input_requires_grad else None
+    gGrid = torch.empty(tuple(grid.shape), dtype=input.dtype, device=input.device) if want_grid else None
+    pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
+    with _on_device(input.device):
+        rc = _lib.load().cs_backward(pb, gs, field.data_ptr() if field is not None else None,
+                                     grid.data_ptr(), offset.data_ptr(),
+                                     acc.data_ptr() if acc is not None else None,
+                                     gGrid.data_ptr() if gGrid is not None else None,
+                                     _cur_stream(input.device))
+    _lib.check(rc, "cs_backward")
+    gInput = _finish_accumulator(acc, input, layout) if acc is not None else None
+    return gInput, gGrid
+
+
+def backward_backward(gOutInput, gOutGrid, input, grid, gOut, offset, padding_mode, align_corners,
+                      input_requires_grad, kernel, multicell, staged=None, want=(True, True, True)):
+    """`_cosine_Xd.backward_backward` (cpp2d:87-106): returns (gInput, gGrid, ggOut).
+    gOutInput is read only when input_requires_grad (mod2d:87); `want` elides outputs."""
+    _check(input, "input")
+    grid, grid_sn = _grid_view(grid)
+    _check(offset, "offset")
+    _check(gOutGrid, "grad_out_grid")
+    dim, N, C, D, H, W, P = _geometry(input, grid)
+    want_input, want_grid, want_ggout = want
+    gOut, gs = _as_stream(gOut, P, "grad_output")
+    need_field = want_grid or want_ggout
+    if need_field:
+        field, layout = _field(input, staged)
+    else:
+        field = None
+        layout = _lib.LAYOUT_CHANNEL_LAST if uses_channel_last(C) else _lib.LAYOUT_CHANNEL_FIRST
+    goi = None
+    if input_requires_grad and gOutInput is not None and need_field:
+        _check(gOutInput, "grad_out_input", contiguous=False)
+        goi = gOutInput.contiguous()
+        if layout == _lib.LAYOUT_CHANNEL_LAST:
+            goi = to_channel_last(goi)
+    acc = _new_accumulator(input, layout) if want_input else None
+    gGrid = torch.empty(tuple(grid.shape), dtype=input.dtype, device=input.device) if want_grid else None
+    ggOut = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device) \
+        if want_ggout else None
+    pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
+    with _on_device(input.device):
+        rc = _lib.load().cs_backward_backward(
+            pb, goi.data_ptr() if goi is not None else None, gOutGrid.data_ptr(),
+            field.data_ptr() if field is not None else None, grid.data_ptr(), gs, offset.data_ptr(),
+            acc.data_ptr() if acc is not None else None,
+            gGrid.data_ptr() if gGrid is not None else None,
+            ggOut.data_ptr() if ggOut is not None else None, _cur_stream(input.device))
+    _lib.check(rc, "cs_backward_backward")
+    gInput = _finish_accumulator(acc, input, layout) if acc is not None else None
+    return gInput, gGrid, ggOut
+
+
+def backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, padding_mode,
+                               align_corners, input_requires_grad, kernel, multicell, staged=None,
+                               want=(True, True), gOutggOut=None):
+    """`_cosine_Xd.backward_backward_backward` (cpp2d:108-127): returns (gInput, ggOut).
+    input_requires_grad is accepted and ignored, as in the reference kernel (cu2d:736).
+    gOutggOut fuses the `b_input` pass of modules_2d.py:109 into the same kernel."""
+    _check(input, "input")
+    grid, grid_sn = _grid_view(grid)
+    _check(offset, "offset")
+    _check(gOutGrid, "gOutGrid")
+    _check(gOutgGrid, "gOutgGrid")
+    dim, N, C, D, H, W, P = _geometry(input, grid)
+    want_input, want_ggout = want
+    gOut, gs = _as_stream(gOut, P, "gOut")
+    if gOutggOut is not None and want_input:
+        gOutggOut, gs2 = _as_stream(gOutggOut, P, "gOutggOut")
+    else:
+        gs2 = _null_stream()
+    if want_ggout:
+        field, layout = _field(input, staged)
+    else:
+        field = None
+        layout = _lib.LAYOUT_CHANNEL_LAST if uses_channel_last(C) else _lib.LAYOUT_CHANNEL_FIRST
+    acc = _new_accumulator(input, layout) if want_input else None
+    ggOut = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device) \
+        if want_ggout else None
+    pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
+    with _on_device(input.device):
+        rc = _lib.load().cs_backward_backward_backward(
+            pb, field.data_ptr() if field is not None else None, grid.data_ptr(), gs,
+            gOutGrid.data_ptr(), gOutgGrid.data_ptr(), gs2, offset.data_ptr(),
+            acc.data_ptr() if acc is not None else None,
+            ggOut.data_ptr() if ggOut is not None else None, _cur_stream(input.device))
+    _lib.check(rc, "cs_backward_backward_backward")
+    gInput = _finish_accumulator(acc, input, layout) if acc is not None else None
+    return gInput, ggOut

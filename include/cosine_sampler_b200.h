@@ -1,0 +1,132 @@
+/*
+ * cosine_sampler_b200.h -- C ABI of libcosine_sampler_b200.so
+ *
+ * Drop-in boundary for the hot path of NamGyuKang/CosineSampler: the four
+ * entry points the reference exports from each of its two pybind modules
+ * (`_cosine_2d`, `_cosine_3d`):
+ *
+ *   forward                     cosine_sampler_2d.cpp:47   cosine_sampler_3d.cpp:50
+ *   backward                    cosine_sampler_2d.cpp:64   cosine_sampler_3d.cpp:67
+ *   backward_backward           cosine_sampler_2d.cpp:87   cosine_sampler_3d.cpp:90
+ *   backward_backward_backward  cosine_sampler_2d.cpp:108  cosine_sampler_3d.cpp:112
+ *   (pybind tables: cosine_sampler_2d.cpp:130-135, cosine_sampler_3d.cpp:133-138)
+ *
+ * re-expressed with plain pointers and sizes: no torch types, no hidden
+ * allocation.  The caller owns every buffer (the reference's extension
+ * allocated its outputs with torch::empty / zeros_like, cpp2d:57,75,80,99-101,
+ * 119-120; here the host layer does that and passes raw device pointers).
+ *
+ * All device buffers are fp32.  All functions launch on `stream` (a
+ * cudaStream_t passed as void*) of the *current* device and return without
+ * synchronising.  Return value: 0 on success, a negative CS_E* code for bad
+ * arguments, a positive cudaError_t when a launch failed.  cs_last_error()
+ * gives a thread-local description of the most recent failure.
+ *
+ * Shapes (reference layouts, contiguous unless a stride is given):
+ *   input / gOutInput / gInput   [N, C, (D,) H, W]      "grid-shaped fields"
+ *   grid / gOutGrid / gOutgGrid / gGrid   [N, P, dim]   P = points per cell
+ *   out / gOut / ggOut / gOutggOut        [N, C, P]     "point streams"
+ *   offset                                [N]
+ * grid[...,0] runs along W, grid[...,1] along H, grid[...,2] along D
+ * (cosine_sampler_2d_kernel.cu:304-308, cosine_sampler_3d_kernel.cu:295-301).
+ */
+#ifndef COSINE_SAMPLER_B200_H
+#define COSINE_SAMPLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_VERSION 100
+
+/* padding_mode_enum, modules_2d.py:4-10 */
+#define CS_PAD_ZEROS 0
+#define CS_PAD_BORDER 1
+#define CS_PAD_REFLECTION 2
+/* kernel_enum, modules_2d.py:12-18 */
+#define CS_KERNEL_COSINE 0
+#define CS_KERNEL_LINEAR 1
+#define CS_KERNEL_SMOOTHSTEP 2
+
+/* Layout of the grid-shaped fields (input, gOutInput, gInput) of one call. */
+#define CS_LAYOUT_CHANNEL_FIRST 0 /* [N, C, (D,) H, W]: the reference boundary layout   */
+#define CS_LAYOUT_CHANNEL_LAST 1  /* [N, (D,) H, W, C]: staged copy, vector gathers/reds */
+
+/* index_mode: how i = ((g+1)/2)*s + offset is rounded. */
+#define CS_INDEX_SEPARATE 0 /* multiply, then add: what test/grid_sampler.py:37-38 does */
+#define CS_INDEX_FUSED 1    /* one fma: what the reference's --use_fast_math build emits */
+
+#define CS_EINVAL (-1)
+#define CS_EUNSUPPORTED (-2)
+
+typedef struct cs_problem {
+    int32_t dim;           /* 2 or 3 */
+    int32_t N;             /* cells (batch of input) */
+    int32_t C;             /* channels */
+    int32_t D, H, W;       /* extent of a cell; D = 1 when dim == 2 */
+    int64_t P;             /* points per cell = prod(grid.shape[1:-1]) */
+    int32_t padding_mode;  /* CS_PAD_* */
+    int32_t align_corners; /* 0/1.  2D forward ignores it and uses 1, as cu2d:307-308 */
+    int32_t kernel;        /* CS_KERNEL_* */
+    int32_t multicell;     /* 0/1: shrink the index range by one cell (cu2d:57-59) */
+    int32_t index_mode;    /* CS_INDEX_* */
+    int32_t field_layout;  /* CS_LAYOUT_* of input, gOutInput and gInput in this call */
+    int64_t grid_stride_n; /* elements between cells of `grid`; P*dim if contiguous, 0 if expanded */
+    int32_t lanes;         /* 0 = auto; else 1,2,4,8 lanes cooperating on one point quad */
+    int32_t reserved;
+} cs_problem;
+
+/* Strided view of a [N, C, P] point stream whose P axis is contiguous.
+ * PIXEL's `val.sum(0)` hands the op a gOut that is expanded along N
+ * (stride_n == 0); the reference copies it (modules_2d.py:42), we read it in place. */
+typedef struct cs_stream {
+    const float *ptr;
+    int64_t stride_n; /* elements */
+    int64_t stride_c; /* elements */
+} cs_stream;
+
+int cs_version(void);
+const char *cs_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t cs_launch_count(void);
+
+/* out[n,c,p] = sum_q input[n,c,corner q] * w_q            (cu2d:265-356, cu3d:250-371) */
+int cs_forward(const cs_problem *pb, const float *input, const float *grid, const float *offset,
+               float *out, void *stream);
+
+/* gInput[n,c,corner q] += w_q gOut[n,c,p]      (nullable: the reference's input_requires_grad)
+ * gGrid[n,p,a] = sum_c gOut sum_q V_q dw_q/dg_a (nullable)   (cu2d:359-507, cu3d:373-584)
+ * gInput must be zero-initialised by the caller (cpp2d:75). */
+int cs_backward(const cs_problem *pb, cs_stream gOut, const float *input, const float *grid,
+                const float *offset, float *gInput, float *gGrid, void *stream);
+
+/* (gInput, gGrid, ggOut) of cu2d:509-717 / cu3d:587-870.  gOutInput nullable (the
+ * reference's input_requires_grad == false); each output nullable = not wanted.
+ * gInput must be zero-initialised by the caller (cpp2d:99). */
+int cs_backward_backward(const cs_problem *pb, const float *gOutInput, const float *gOutGrid,
+                         const float *input, const float *grid, cs_stream gOut,
+                         const float *offset, float *gInput, float *gGrid, float *ggOut,
+                         void *stream);
+
+/* (gInput, ggOut) of cu2d:722-891 / cu3d:875-1071.  Either output nullable.
+ * gOutggOut (nullable) fuses the second call of modules_2d.py:109 into the same pass:
+ * gInput += scatter(gOutggOut * sum_a dw_q/dg_a gOutGrid_a), i.e. `gInput + b_input`
+ * of modules_2d.py:111 in one kernel.  gInput must be zero-initialised by the caller. */
+int cs_backward_backward_backward(const cs_problem *pb, const float *input, const float *grid,
+                                  cs_stream gOut, const float *gOutGrid, const float *gOutgGrid,
+                                  cs_stream gOutggOut, const float *offset, float *gInput,
+                                  float *ggOut, void *stream);
+
+/* Staging between the reference layout and the channel-last layout.
+ * src [N, C, T] -> dst [N, T, C]   (T = D*H*W) */
+int cs_to_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T, void *stream);
+/* src [N, T, C] -> dst [N, C, T]; accumulate != 0 adds into dst instead of overwriting */
+int cs_from_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T,
+                         int32_t accumulate, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSINE_SAMPLER_B200_H */
