@@ -65,6 +65,7 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     if (pb->field_layout == CS_LAYOUT_CHANNEL_LAST) { p.texel_stride = pb->C; p.chan_stride = 1; }
     else { p.texel_stride = 1; p.chan_stride = (int)T; }
     p.grid = grid; p.grid_sn = pb->grid_stride_n; p.offset = offset;
+    p.grid_vec2 = ((reinterpret_cast<uintptr_t>(grid) & 7u) == 0) && (pb->grid_stride_n % 2 == 0);
     p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
     p.multicell = pb->multicell; p.index_mode = pb->index_mode;
     return 0;

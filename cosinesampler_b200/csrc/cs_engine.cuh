@@ -63,6 +63,7 @@ struct StageParams {
     int svec4;                                 // streams may be accessed as float4
     // per-point arrays
     const float* grid; long long grid_sn;      // [N,P,dim]
+    int grid_vec2;                             // 2D coordinates may be loaded as float2
     const float* gog;                          // gOutGrid  [N,P,dim]
     const float* gogg;                         // gOutgGrid [N,P,dim]
     float* ggrid;                              // gGrid [N,P,dim] or nullptr
@@ -270,7 +271,7 @@ cs_stage_kernel(const StageParams p) {
             if (pi < p.P) {
                 const float* gp = p.grid + (long long)n * p.grid_sn + pi * DIM;
                 float g[DIM];
-                if (DIM == 2) {
+                if (DIM == 2 && p.grid_vec2) {
                     const float2 t = __ldg(reinterpret_cast<const float2*>(gp));
                     g[0] = t.x; g[1] = t.y;
                 } else {

@@ -18,6 +18,40 @@ _INDEX_MODE = _lib.INDEX_FUSED if os.environ.get("COSINE_SAMPLER_INDEX_MODE", ""
 _LANES = int(os.environ.get("COSINE_SAMPLER_LANES", "0"))
 
 
+# Optional per-call timing: bench.py sets `profiler` to an object with
+# `record(label, algorithmic_bytes, start_event, end_event)`; events are recorded on
+# the stream the kernel is launched on.
+profiler = None
+
+
+class _timed:
+    """Brackets one stage call with CUDA events when a profiler is installed."""
+    __slots__ = ("label", "nbytes", "device", "start")
+
+    def __init__(self, label, nbytes, device):
+        self.label, self.nbytes, self.device, self.start = label, nbytes, device, None
+
+    def __enter__(self):
+        if profiler is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *a):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.device))
+            profiler.record(self.label, self.nbytes, self.start, end)
+
+
+def algorithmic_bytes(dim, N, C, P, T, streams, per_point, fields):
+    """Algorithmic bytes of one stage call: every tensor crossing the
+    operator boundary counted once.  streams = number of [N,C,P] tensors read or written,
+    per_point = number of [N,P,dim] tensors (coordinates included), fields = number of
+    grid-shaped [N,C,T] tensors read or produced."""
+    return 4 * (N * P * (C * streams + dim * per_point) + fields * N * C * T)
+
+
 def set_index_mode(mode):
     """'separate' (default; rounds like test/grid_sampler.py:37-38) or 'fused'
     (one fma, like the reference CUDA build with --use_fast_math).  SURVEY 7.1."""
@@ -231,7 +265,8 @@ def forward(input, grid, offset, padding_mode, align_corners, kernel, multicell,
     field, layout = _field(input, staged)
     out = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device)
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
-    with _on_device(input.device):
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, streams=1, per_point=1, fields=1)
+    with _on_device(input.device), _timed("F%dd" % dim, nbytes, input.device):
         rc = _lib.load().cs_forward(pb, field.data_ptr(), grid.data_ptr(), offset.data_ptr(),
                                     out.data_ptr(), _cur_stream(input.device))
     _lib.check(rc, "cs_forward")
@@ -255,7 +290,10 @@ def backward(gOut, input, grid, offset, padding_mode, align_corners, input_requi
     acc = _new_accumulator(input, layout) if input_requires_grad else None
     gGrid = torch.empty(tuple(grid.shape), dtype=input.dtype, device=input.device) if want_grid else None
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
-    with _on_device(input.device):
+    label = "B%dd[%s%s]" % (dim, "I" if acc is not None else "", "G" if want_grid else "")
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, streams=1, per_point=1 + (1 if want_grid else 0),
+                               fields=(1 if want_grid else 0) + (1 if acc is not None else 0))
+    with _on_device(input.device), _timed(label, nbytes, input.device):
         rc = _lib.load().cs_backward(pb, gs, field.data_ptr() if field is not None else None,
                                      grid.data_ptr(), offset.data_ptr(),
                                      acc.data_ptr() if acc is not None else None,
@@ -294,7 +332,13 @@ def backward_backward(gOutInput, gOutGrid, input, grid, gOut, offset, padding_mo
     ggOut = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device) \
         if want_ggout else None
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
-    with _on_device(input.device):
+    label = "BB%dd[%s%s%s%s]" % (dim, "I" if want_input else "", "G" if want_grid else "",
+                                 "O" if want_ggout else "", "+U" if goi is not None else "")
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, streams=1 + (1 if want_ggout else 0),
+                               per_point=2 + (1 if want_grid else 0),
+                               fields=(1 if need_field else 0) + (1 if want_input else 0)
+                               + (1 if goi is not None else 0))
+    with _on_device(input.device), _timed(label, nbytes, input.device):
         rc = _lib.load().cs_backward_backward(
             pb, goi.data_ptr() if goi is not None else None, gOutGrid.data_ptr(),
             field.data_ptr() if field is not None else None, grid.data_ptr(), gs, offset.data_ptr(),
@@ -333,7 +377,13 @@ def backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, p
     ggOut = torch.empty((N, C) + tuple(grid.shape[1:-1]), dtype=input.dtype, device=input.device) \
         if want_ggout else None
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
-    with _on_device(input.device):
+    fused = gs2.ptr is not None
+    label = "BBB%dd[%s%s%s]" % (dim, "I" if want_input else "", "O" if want_ggout else "",
+                                "+X2" if fused else "")
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W,
+                               streams=1 + (1 if want_ggout else 0) + (1 if fused else 0), per_point=3,
+                               fields=(1 if want_ggout else 0) + (1 if want_input else 0))
+    with _on_device(input.device), _timed(label, nbytes, input.device):
         rc = _lib.load().cs_backward_backward_backward(
             pb, field.data_ptr() if field is not None else None, grid.data_ptr(), gs,
             gOutGrid.data_ptr(), gOutgGrid.data_ptr(), gs2, offset.data_ptr(),

@@ -1,0 +1,75 @@
+"""The C-ABI library loads, exports every symbol include/cosine_sampler_b200.h declares,
+and the ctypes mirror of its structs matches the C layout.  No compute calls (no GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cosine_sampler_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cs_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_four_entry_points():
+    names = _declared_functions()
+    for n in ("cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
+              "cs_to_channel_last", "cs_from_channel_last", "cs_last_error", "cs_version",
+              "cs_launch_count"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert set(declared) == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None, name
+    assert lib.cs_version() == 100
+    assert lib.cs_launch_count() == 0 or lib.cs_launch_count() > 0   # callable without a GPU
+
+
+def test_struct_layout_matches_c(tmp_path):
+    from cosinesampler_b200 import _lib
+    prog = tmp_path / "layout.c"
+    prog.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "cosine_sampler_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(cs_problem), offsetof(cs_problem, P),
+         offsetof(cs_problem, padding_mode), offsetof(cs_problem, field_layout),
+         offsetof(cs_problem, grid_stride_n), offsetof(cs_problem, lanes), sizeof(cs_stream));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    P = _lib.Problem
+    want = [ctypes.sizeof(P), P.P.offset, P.padding_mode.offset, P.field_layout.offset,
+            P.grid_stride_n.offset, P.lanes.offset, ctypes.sizeof(_lib.Stream3)]
+    assert got == want
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    """argument validation happens before any CUDA call"""
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    pb = _lib.Problem()
+    pb.dim = 4
+    rc = lib.cs_forward(ctypes.byref(pb), None, None, None, None, None)
+    assert rc == -1
+    assert b"dim" in lib.cs_last_error()
+    pb.dim, pb.N, pb.C, pb.D, pb.H, pb.W, pb.P = 2, 1, 4, 1, 8, 8, 16
+    rc = lib.cs_forward(ctypes.byref(pb), None, None, None, None, None)
+    assert rc == -1 and b"NULL" in lib.cs_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "cs_forward")
