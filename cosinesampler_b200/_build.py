@@ -12,7 +12,12 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_NAME = "libcosine_sampler_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
-SOURCES = ["cs_api.cu", "cs_stage_2d.cu", "cs_stage_3d.cu"]
+# (source, object name, extra defines): the stage engine is compiled once per variant
+VARIANTS = [(d, 4, l) for d in (2, 3) for l in (0, 1, 2, 3)] + [(2, 1, 0), (3, 1, 0)]
+UNITS = [("cs_api.cu", "cs_api.o", [])] + [
+    ("cs_stage_inst.cu", "cs_stage_d%d_v%d_l%d.o" % v,
+     ["-DCS_DIM=%d" % v[0], "-DCS_VEC=%d" % v[1], "-DCS_LSHIFT=%d" % v[2]]) for v in VARIANTS]
+SOURCES = ["cs_api.cu", "cs_stage_inst.cu"]
 HEADERS = ["cs_engine.cuh", "cs_launch.cuh", os.path.join("..", "..", "include", "cosine_sampler_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -33,37 +38,51 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), out_path=None):
+    """Compile the library if it is missing or older than its sources.
+    `defines` / `out_path` build an experimental variant next to the default library."""
+    if out_path is None:
+        out_path = LIB_PATH
+    if not force and not defines and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
-    objdir = os.path.join(PKG_DIR, "build")
+    objdir = os.path.join(PKG_DIR, "build" if out_path == LIB_PATH else
+                          "build_" + os.path.basename(out_path).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
     logs = {}
+    extra_defines = tuple(defines)
 
-    def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(unit):
+        src, objname, defines = unit
+        obj = os.path.join(objdir, objname)
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_defines) + defines + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        logs[src] = r.stdout + r.stderr
+        logs[objname] = r.stdout + r.stderr
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (src, logs[src]))
+            raise RuntimeError("nvcc failed for %s:\n%s" % (objname, logs[objname]))
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
+    cmd = [nvcc, "-shared", "-o", out_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s%s" % (r.stdout, r.stderr))
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
-        for src in SOURCES:
-            f.write("==== %s ====\n%s\n" % (src, logs[src]))
+        for _, objname, _ in UNITS:
+            f.write("==== %s ====\n%s\n" % (objname, logs[objname]))
     if verbose:
-        print("built", LIB_PATH)
-    return LIB_PATH
+        print("built", out_path)
+    return out_path
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    # python -m cosinesampler_b200._build [--force] [--variant NAME -DFOO=1 ...]
+    argv = sys.argv[1:]
+    if "--variant" in argv:
+        name = argv[argv.index("--variant") + 1]
+        defs = [a for a in argv if a.startswith("-D")]
+        build(force=True, verbose=True, defines=defs,
+              out_path=os.path.join(PKG_DIR, "libcosine_sampler_b200_%s.so" % name))
+    else:
+        build(force="--force" in argv, verbose=True)

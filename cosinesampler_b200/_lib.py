@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libcosine_sampler_b200.so")
+# COSINE_SAMPLER_LIB selects an experimental build variant of the same library (tools/)
+LIB_PATH = os.environ.get("COSINE_SAMPLER_LIB") or os.path.join(_PKG_DIR, "libcosine_sampler_b200.so")
 
 # every symbol include/cosine_sampler_b200.h declares
 EXPORTS = (

@@ -10,8 +10,12 @@
 #include "cs_engine.cuh"
 
 namespace cs {
-cudaError_t launch_stage_2d(int vec, int stage, bool has_u, bool has_x2, const StageParams& p, cudaStream_t s);
-cudaError_t launch_stage_3d(int vec, int stage, bool has_u, bool has_x2, const StageParams& p, cudaStream_t s);
+// one function per (dim, field vector width, log2 lanes) variant, each in its own object file
+#define CS_DECL(name) cudaError_t name(int stage, bool has_u, bool has_x2, const StageParams& p, cudaStream_t s);
+CS_DECL(launch_d2_v4_l0) CS_DECL(launch_d2_v4_l1) CS_DECL(launch_d2_v4_l2) CS_DECL(launch_d2_v4_l3)
+CS_DECL(launch_d3_v4_l0) CS_DECL(launch_d3_v4_l1) CS_DECL(launch_d3_v4_l2) CS_DECL(launch_d3_v4_l3)
+CS_DECL(launch_d2_v1_l0) CS_DECL(launch_d3_v1_l0)
+#undef CS_DECL
 }  // namespace cs
 
 namespace {
@@ -40,6 +44,8 @@ int gcd8(int v) {  // largest power of two <= 8 dividing v
     return l;
 }
 
+constexpr int CS_NOTHING_TO_DO = 1 << 30;   // internal: valid but empty problem
+
 // Validate the problem and fill the geometry part of StageParams.
 int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const float* offset) {
     if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
@@ -53,6 +59,7 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     if (pb->field_layout < 0 || pb->field_layout > 1) return fail(CS_EINVAL, "bad field_layout %d", pb->field_layout);
     if (pb->lanes != 0 && pb->lanes != 1 && pb->lanes != 2 && pb->lanes != 4 && pb->lanes != 8)
         return fail(CS_EINVAL, "lanes must be 0,1,2,4 or 8");
+    if (pb->N == 0 || pb->C == 0 || pb->P == 0) return CS_NOTHING_TO_DO;   // empty problem (cu2d:904)
     if (!grid || !offset) return fail(CS_EINVAL, "grid/offset pointer is NULL");
     const long long T = (long long)pb->D * pb->H * pb->W;
     if (T * (long long)pb->C >= (1ll << 31))
@@ -81,16 +88,22 @@ int run(const cs_problem* pb, cs::StageParams& p, int stage, bool has_u, bool ha
     bool vec4 = (pb->field_layout == CS_LAYOUT_CHANNEL_LAST) && (p.C % 4 == 0) &&
                 aligned16(p.V) && aligned16(p.U) && aligned16(p.acc);
     const int vec = vec4 ? 4 : 1;
-    int lanes = pb->lanes ? pb->lanes : gcd8(p.C / vec);
+    // scalar fields: one lane walks all channels of its point quad (channel-first strides
+    // give the lanes of a quad nothing to share)
+    int lanes = vec4 ? (pb->lanes ? pb->lanes : gcd8(p.C / 4)) : 1;
     p.lshift = (lanes == 1) ? 0 : (lanes == 2) ? 1 : (lanes == 4) ? 2 : 3;
     const int pts = 128 >> p.lshift;
     p.num_ptiles = (p.P + pts - 1) / pts;
     // stream vector width
     p.svec4 = (p.P % 4 == 0) && aligned16(p.x1) && aligned16(p.x2) && aligned16(p.y) &&
               p.x1_sn % 4 == 0 && p.x1_sc % 4 == 0 && p.x2_sn % 4 == 0 && p.x2_sc % 4 == 0;
-    cudaError_t e = (pb->dim == 2)
-        ? cs::launch_stage_2d(vec, stage, has_u, has_x2, p, (cudaStream_t)stream)
-        : cs::launch_stage_3d(vec, stage, has_u, has_x2, p, (cudaStream_t)stream);
+    p.gvec4 = (p.P % 4 == 0) && aligned16(p.ggrid);
+    using Fn = cudaError_t (*)(int, bool, bool, const cs::StageParams&, cudaStream_t);
+    static const Fn table[2][5] = {
+        {cs::launch_d2_v4_l0, cs::launch_d2_v4_l1, cs::launch_d2_v4_l2, cs::launch_d2_v4_l3, cs::launch_d2_v1_l0},
+        {cs::launch_d3_v4_l0, cs::launch_d3_v4_l1, cs::launch_d3_v4_l2, cs::launch_d3_v4_l3, cs::launch_d3_v1_l0}};
+    const Fn fn = table[pb->dim - 2][vec4 ? p.lshift : 4];
+    cudaError_t e = fn(stage, has_u, has_x2, p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "stage kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -166,7 +179,7 @@ uint64_t cs_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 int cs_forward(const cs_problem* pb, const float* input, const float* grid, const float* offset,
                float* out, void* stream) {
     cs::StageParams p;
-    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (int rc = setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
     if (!input || !out) return fail(CS_EINVAL, "cs_forward: input/out is NULL");
     p.V = input; p.y = out;
     return run(pb, p, cs::ST_F, false, false, stream);
@@ -175,7 +188,7 @@ int cs_forward(const cs_problem* pb, const float* input, const float* grid, cons
 int cs_backward(const cs_problem* pb, cs_stream gOut, const float* input, const float* grid,
                 const float* offset, float* gInput, float* gGrid, void* stream) {
     cs::StageParams p;
-    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (int rc = setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
     if (!gOut.ptr) return fail(CS_EINVAL, "cs_backward: gOut is NULL");
     if (gGrid && !input) return fail(CS_EINVAL, "cs_backward: gGrid needs input");
     if (!gInput && !gGrid) return 0;
@@ -188,7 +201,7 @@ int cs_backward_backward(const cs_problem* pb, const float* gOutInput, const flo
                          const float* input, const float* grid, cs_stream gOut, const float* offset,
                          float* gInput, float* gGrid, float* ggOut, void* stream) {
     cs::StageParams p;
-    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (int rc = setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
     if (!gOut.ptr || !gOutGrid) return fail(CS_EINVAL, "cs_backward_backward: gOut/gOutGrid is NULL");
     if ((gGrid || ggOut) && !input) return fail(CS_EINVAL, "cs_backward_backward: gGrid/ggOut need input");
     if (!gInput && !gGrid && !ggOut) return 0;
@@ -205,7 +218,7 @@ int cs_backward_backward_backward(const cs_problem* pb, const float* input, cons
                                   cs_stream gOutggOut, const float* offset, float* gInput,
                                   float* ggOut, void* stream) {
     cs::StageParams p;
-    if (int rc = setup(pb, p, grid, offset)) return rc;
+    if (int rc = setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
     if (!gOut.ptr || !gOutGrid || !gOutgGrid)
         return fail(CS_EINVAL, "cs_backward_backward_backward: gOut/gOutGrid/gOutgGrid is NULL");
     if (ggOut && !input) return fail(CS_EINVAL, "cs_backward_backward_backward: ggOut needs input");

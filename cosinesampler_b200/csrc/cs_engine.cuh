@@ -26,10 +26,12 @@
 //     [N,C,P] stream is a 16-byte access and the 32/L quads of a warp cover
 //     contiguous 128*(4/L)-byte runs per channel: streams stay fully coalesced
 //     in their reference layout.
-//   * phase 1 of a tile computes the per-point record (index map, padding,
-//     kernel values) once per point, one point per lane, into shared memory;
-//     phase 2 reads it back as broadcasts.  The transcendental work is thus
-//     never replicated across the lanes of a quad.
+//   * phase 1 of a tile computes, once per point (one point per lane), the index
+//     map, padding, kernel values AND the finished per-corner coefficients of
+//     the stage into a shared-memory record; phase 2 reads them back as
+//     128-bit broadcasts (one float4 = the 4 corners of a coefficient).  Neither
+//     the transcendental work nor the coefficient products are replicated over
+//     the L lanes of a quad, and phase 2 is nothing but address + gather + fma.
 //   * persistent grid: blocks loop over tiles, cell index fastest so that the N
 //     cells of one point (which share coordinates and an expanded gOut in
 //     PIXEL) are in flight together.
@@ -61,6 +63,7 @@ struct StageParams {
     const float* x2; long long x2_sn, x2_sc;   // gOutggOut (BBB fused b_input) or nullptr
     float* y;                                  // out / ggOut (contiguous [N,C,P]) or nullptr
     int svec4;                                 // streams may be accessed as float4
+    int gvec4;                                 // gGrid quads may be stored as float4
     // per-point arrays
     const float* grid; long long grid_sn;      // [N,P,dim]
     int grid_vec2;                             // 2D coordinates may be loaded as float2
@@ -212,126 +215,367 @@ template <> struct FieldVec<1> {
     __device__ __forceinline__ static void red(float* p, const float (&a)[1]) { red_add_f32(p, a[0]); }
 };
 
-// record layout in shared memory: SoA, rec[field * pts + point]
-//   field 0: base texel (int bits)   field 1: corner-valid mask (int bits)
-//   then per axis a: w0, w1 [, d [, e]] and stage extras
-template <int DIM, int STAGE, bool HAS_X2> struct RecLayout {
-    // per-axis fields
-    static constexpr int W0 = 0, W1 = 1, D1 = 2, E2 = 3, G1 = 4, G2 = 5;
-    // number of per-axis fields by stage
-    //  F: w0 w1                     B: w0 w1 d
-    //  BB: w0 w1 d e gog            BBB: w0 w1 e*gog*gogg [d*gog]
-    static constexpr int PER_AXIS = (STAGE == ST_F) ? 2 : (STAGE == ST_B) ? 3 :
-                                    (STAGE == ST_BB) ? 5 : (HAS_X2 ? 4 : 3);
-    static constexpr int FIELDS = 2 + DIM * PER_AXIS;
+// Record layout in shared memory: float4 fields, rec4[field * PTS + point].
+//   field 0            : (base texel, corner-valid mask, -, -) as int bits
+//   field 1 + k*CQ + h : coefficient k for corners 4h..4h+3   (CQ = corner quads = NCORN/4)
+// Coefficient index k by stage:
+//   F   : 0 = w_q
+//   B   : 0 = w_q (scatter)            1+a = D_a,q (gGrid)
+//   BB  : 0 = A_q (ggOut and scatter)  1+a = cg_a,q (gGrid)   [U: 1+DIM = w_q ; 3D: 2+DIM+a = D_a,q]
+//   BBB : 0 = E_q (ggOut and scatter)  [X2: 1 = A_q]
+template <int DIM, int STAGE, bool HAS_U, bool HAS_X2> struct RecLayout {
+    static constexpr int NCORN = 1 << DIM;
+    static constexpr int CQ = NCORN / 4;
+    static constexpr int K = (STAGE == ST_F) ? 1 : (STAGE == ST_B) ? 1 + DIM :
+                             (STAGE == ST_BB) ? (1 + DIM + (HAS_U ? 1 + (DIM == 3 ? DIM : 0) : 0))
+                                              : (HAS_X2 ? 2 : 1);
+    static constexpr int FIELDS4 = 1 + K * CQ;           // float4 fields per point
 };
 
-// ---------------------------------------------------------------------------
-// The stage kernel
-// ---------------------------------------------------------------------------
-template <int DIM, int VEC, int STAGE, bool HAS_U, bool HAS_X2>
-__global__ void __launch_bounds__(256)
-cs_stage_kernel(const StageParams p) {
-    using RL = RecLayout<DIM, STAGE, HAS_X2>;
-    constexpr int NCORN = 1 << DIM;
-    constexpr int PA = RL::PER_AXIS;
-    constexpr bool HAS_X1 = (STAGE != ST_F);
+// Per-point inputs of phase 1, prefetched one tile ahead so that their latency hides
+// behind phase 2 of the current tile.
+template <int DIM, int STAGE> struct PointIn {
+    float g[DIM];
+    float gog[(STAGE >= ST_BB) ? DIM : 1];
+    float gogg[(STAGE == ST_BBB) ? DIM : 1];
+};
 
-    extern __shared__ float smem[];
+template <int DIM, int STAGE>
+__device__ __forceinline__ void load_point(PointIn<DIM, STAGE>& in, const StageParams& p, int n,
+                                           long long pi) {
+    if (pi < p.P) {
+        const float* gp = p.grid + (long long)n * p.grid_sn + pi * DIM;
+        if (DIM == 2 && p.grid_vec2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(gp));
+            in.g[0] = t.x; in.g[1] = t.y;
+        } else {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) in.g[a] = __ldg(gp + a);
+        }
+        if (STAGE >= ST_BB) {
+            const float* s = p.gog + ((long long)n * p.P + pi) * DIM;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) in.gog[a] = __ldg(s + a);
+        }
+        if (STAGE == ST_BBB) {
+            const float* s = p.gogg + ((long long)n * p.P + pi) * DIM;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) in.gogg[a] = __ldg(s + a);
+        }
+    }
+}
+
+// Phase 1 for one point: index map -> per-corner coefficients -> shared-memory record.
+template <int DIM, int STAGE, bool HAS_U, bool HAS_X2, int PTS>
+__device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<DIM, STAGE>& in,
+                                             bool in_range, float off, const StageParams& p, bool align) {
+    using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
+    constexpr int NCORN = RL::NCORN;
+    constexpr int CQ = RL::CQ;
+    constexpr int K = RL::K;
+    constexpr int ORDER = (STAGE == ST_F) ? 0 : (STAGE == ST_B) ? 1 : 2;
+    int base = 0, mask = 0;
+    float coef[K][NCORN];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) coef[k][c] = 0.f;
+    if (in_range) {
+        bool ok = true;
+        bool lo_ok[DIM], hi_ok[DIM];
+        float w[DIM][2], dw[DIM][2], ew[DIM][2];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            const AxisRec ar = axis_setup(in.g[a], p.size[a], off, p, align, ORDER);
+            ok = ok && ar.ok;
+            base += ar.l * p.tstride[a];
+            lo_ok[a] = (ar.l >= 0) && (ar.l < p.size[a]);
+            hi_ok[a] = (ar.l + 1 >= 0) && (ar.l + 1 < p.size[a]);
+            w[a][0] = ar.w0; w[a][1] = ar.w1;
+            if (ORDER >= 1) { dw[a][0] = -ar.d; dw[a][1] = ar.d; }
+            if (ORDER >= 2) { ew[a][0] = ar.e; ew[a][1] = -ar.e; }
+        }
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) {
+            int b[DIM];
+            bool valid = ok;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) { b[a] = (c >> a) & 1; valid = valid && (b[a] ? hi_ok[a] : lo_ok[a]); }
+            if (!valid) continue;
+            mask |= 1 << c;
+            float wo[DIM];          // prod_{c != a} W_c
+            float wall;             // prod_a W_a, in x,y,z order
+            if (DIM == 2) {
+                wo[0] = w[1][b[1]]; wo[1] = w[0][b[0]];
+                wall = w[0][b[0]] * w[1][b[1]];
+            } else {
+                wo[0] = w[1][b[1]] * w[2][b[2]];
+                wo[1] = w[0][b[0]] * w[2][b[2]];
+                wo[2] = w[0][b[0]] * w[1][b[1]];
+                wall = (w[0][b[0]] * w[1][b[1]]) * w[2][b[2]];
+            }
+            if (STAGE == ST_F) {
+                coef[0][c] = wall;
+            } else if (STAGE == ST_B) {
+                coef[0][c] = wall;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) coef[1 + a][c] = dw[a][b[a]] * wo[a];
+            } else if (STAGE == ST_BB) {
+                float A = 0.f;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) A += dw[a][b[a]] * wo[a] * in.gog[a];
+                coef[0][c] = A;
+                if (DIM == 2) {
+                    // pure second derivatives only (cu2d:705-706)
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) coef[1 + a][c] = ew[a][b[a]] * wo[a] * in.gog[a];
+                } else {
+                    // full Hessian row (cu3d:848-856)
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) {
+                        float sacc = ew[a][b[a]] * wo[a] * in.gog[a];
+#pragma unroll
+                        for (int bb = 0; bb < DIM; ++bb) {
+                            if (bb == a) continue;
+                            const int cc = 3 - a - bb;
+                            sacc += dw[a][b[a]] * dw[bb][b[bb]] * w[cc][b[cc]] * in.gog[bb];
+                        }
+                        coef[1 + a][c] = sacc;
+                    }
+                }
+                if (HAS_U) {
+                    coef[1 + DIM][c] = wall;                             // ggOut += gOutInput * w_q
+                    if (DIM == 3) {                                      // gGrid += <gOutInput, gOut> D_a,q (cu3d:836-840)
+#pragma unroll
+                        for (int a = 0; a < DIM; ++a) coef[2 + DIM + a][c] = dw[a][b[a]] * wo[a];
+                    }
+                }
+            } else {  // BBB: pure second derivatives (cu2d:876-885, cu3d:1054-1065)
+                float E = 0.f, A = 0.f;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    E += ew[a][b[a]] * wo[a] * (in.gogg[a] * in.gog[a]);
+                    if (HAS_X2) A += dw[a][b[a]] * wo[a] * in.gog[a];
+                }
+                coef[0][c] = E;
+                if (HAS_X2) coef[1][c] = A;
+            }
+        }
+    }
+    rec4[i] = make_float4(__int_as_float(base), __int_as_float(mask), 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int h = 0; h < CQ; ++h)
+            rec4[(1 + k * CQ + h) * PTS + i] =
+                make_float4(coef[k][4 * h], coef[k][4 * h + 1], coef[k][4 * h + 2], coef[k][4 * h + 3]);
+}
+
+__device__ __forceinline__ float f4get(const float4& v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
+// ---------------------------------------------------------------------------
+// The stage kernel: a per-warp software pipeline
+//
+//   work item  = (tile, channel-vector iteration jj); a tile is PTS points of one cell
+//   stage      = PG of the 4 points a lane owns in the item (NST = 4/PG stages per item)
+//
+// Everything a stage needs from global memory -- the 2^dim corner vectors of PG points
+// (and of gOutInput), plus once per item the lane's slice of the gOut / gOutggOut
+// streams -- is fetched with cp.async (LDGSTS, 16 B per lane, zero-fill for corners that
+// are out of bounds) into lane-private shared-memory slots, one stage ahead of its use.
+// The data in flight lives in shared memory, not in registers, so a warp keeps
+// PG*2^dim*16 B per lane in flight while it computes the previous stage, and phase 1 of
+// the next tile (index map, sincospif, coefficients) also overlaps the gathers.
+// ---------------------------------------------------------------------------
+#ifndef CS_THREADS
+#define CS_THREADS 256
+#endif
+#ifndef CS_MIN_BLOCKS
+#define CS_MIN_BLOCKS 1
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;                       // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+// Shared-memory plan of one warp (in float4 units).
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2> struct WarpSmem {
+    using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
+    static constexpr int NCORN = 1 << DIM;
+    static constexpr int PTS = 128 >> LSHIFT;
+    static constexpr int PG = (DIM == 2) ? 2 : 1;            // points per stage
+    static constexpr int NST = 4 / PG;
+    static constexpr int GSLOTS = PG * NCORN * (HAS_U ? 2 : 1);   // gather slots per stage (V then U)
+    static constexpr int XSLOTS = (STAGE == ST_F) ? 0 : VEC * (HAS_X2 ? 2 : 1);   // stream slots per item
+    static constexpr int REC = 2 * RL::FIELDS4 * PTS;        // records, double-buffered by tile
+    static constexpr int GBUF = 2 * GSLOTS * 32;             // gathers, double-buffered by stage
+    static constexpr int XBUF = 2 * XSLOTS * 32;             // streams, double-buffered by item
+    static constexpr int TOTAL = REC + GBUF + XBUF;          // float4 per warp
+};
+
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
+__global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS)
+cs_stage_kernel(const StageParams p) {
+    using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
+    using WS = WarpSmem<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
+    constexpr int NCORN = 1 << DIM;
+    constexpr int CQ = RL::CQ;
+    constexpr bool HAS_X1 = (STAGE != ST_F);
+    constexpr int L = 1 << LSHIFT;                 // lanes per point quad
+    constexpr int PTS = WS::PTS;                   // points per warp tile
+    constexpr int PPL = (PTS + 31) / 32;           // points per lane in phase 1
+    constexpr int PG = WS::PG;
+    constexpr int NST = WS::NST;
+    constexpr int F4 = RL::FIELDS4;
+
+    extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int L = 1 << p.lshift;
-    const int pts = 128 >> p.lshift;               // points per tile
-    const int q = lane >> p.lshift;                // quad within the tile
+    const int q = lane >> LSHIFT;                  // quad within the tile
     const int j = lane & (L - 1);                  // lane within the quad
-    float* rec = smem + (size_t)warp * RL::FIELDS * pts;
+    float4* wbase = smem4 + (size_t)warp * WS::TOTAL;
+    float4* recbuf = wbase;                        // [2][F4][PTS]
+    float4* gbuf = wbase + WS::REC;                // [2][GSLOTS][32]
+    float4* xbuf = gbuf + WS::GBUF;                // [2][XSLOTS][32]
 
     const bool want_y = (p.y != nullptr);
-    const bool want_g = (p.ggrid != nullptr);
-    const bool want_s = (p.acc != nullptr);
+    const bool want_g = (p.ggrid != nullptr) && (STAGE == ST_B || STAGE == ST_BB);
+    const bool want_s = (p.acc != nullptr) && HAS_X1;
     const bool need_v = want_y || want_g;
     const bool svec = p.svec4 != 0;
     const int V = p.C / VEC;                       // channel vectors per texel
+    const int njj = (V - j + L - 1) / L;           // items per tile for this lane (same for all lanes when L | V)
     // 2D forward always maps with align_corners = 1 (cu2d:307-308)
     const bool align = (STAGE == ST_F && DIM == 2) ? true : (p.align != 0);
-    constexpr int ORDER = (STAGE == ST_F) ? 0 : (STAGE == ST_B) ? 1 : 2;
+
+    int coff[NCORN];                               // texel offset of each corner
+#pragma unroll
+    for (int c = 0; c < NCORN; ++c) {
+        coff[c] = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) coff[c] += ((c >> a) & 1) * p.tstride[a];
+    }
 
     const long long total = p.num_ptiles * p.N;
-    for (long long tile = (long long)blockIdx.x * wpb + warp; tile < total;
-         tile += (long long)gridDim.x * wpb) {
-        const int n = (int)(tile % p.N);
-        const long long pt0 = (tile / p.N) * pts;
+    const long long tstep = (long long)gridDim.x * wpb;
+    long long tile = (long long)blockIdx.x * wpb + warp;
+    if (tile >= total) return;
+    // all lanes of a warp must run the same number of items (warp-level syncs inside):
+    // lanes with no channel work (j >= V) still walk the pipeline with empty stages
+    const int items_per_tile = (V + L - 1) / L;
 
-        // ---------------- phase 1: one point per lane -> record -------------
+    PointIn<DIM, STAGE> pin[PPL];
+
+    // ---- helpers ---------------------------------------------------------------------
+    auto load_inputs = [&](long long tl) {
+        const int n = (int)(tl % p.N);
+        const long long pt0 = (tl / p.N) * PTS;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u)
+            if (u * 32 + lane < PTS) load_point<DIM, STAGE>(pin[u], p, n, pt0 + u * 32 + lane);
+    };
+    auto phase1 = [&](long long tl, int par) {
+        const int n = (int)(tl % p.N);
+        const long long pt0 = (tl / p.N) * PTS;
         const float off = __ldg(p.offset + n);
-        for (int i = lane; i < pts; i += 32) {
-            const long long pi = pt0 + i;
-            int base = 0, mask = 0;
-            if (pi < p.P) {
-                const float* gp = p.grid + (long long)n * p.grid_sn + pi * DIM;
-                float g[DIM];
-                if (DIM == 2 && p.grid_vec2) {
-                    const float2 t = __ldg(reinterpret_cast<const float2*>(gp));
-                    g[0] = t.x; g[1] = t.y;
-                } else {
+        __syncwarp();                               // everyone is done reading this record buffer
 #pragma unroll
-                    for (int a = 0; a < DIM; ++a) g[a] = __ldg(gp + a);
-                }
-                float gog[DIM], gogg[DIM];
-                if (STAGE >= ST_BB) {
-                    const float* s = p.gog + ((long long)n * p.P + pi) * DIM;
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) gog[a] = __ldg(s + a);
-                }
-                if (STAGE == ST_BBB) {
-                    const float* s = p.gogg + ((long long)n * p.P + pi) * DIM;
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) gogg[a] = __ldg(s + a);
-                }
-                bool ok = true;
-                int lo_ok[DIM], hi_ok[DIM];
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const AxisRec ar = axis_setup(g[a], p.size[a], off, p, align, ORDER);
-                    ok = ok && ar.ok;
-                    base += ar.l * p.tstride[a];
-                    lo_ok[a] = (ar.l >= 0) && (ar.l < p.size[a]);
-                    hi_ok[a] = (ar.l + 1 >= 0) && (ar.l + 1 < p.size[a]);
-                    float* ra = rec + (2 + a * PA) * pts + i;
-                    ra[RL::W0 * pts] = ar.w0;
-                    ra[RL::W1 * pts] = ar.w1;
-                    if (STAGE == ST_B) ra[2 * pts] = ar.d;
-                    if (STAGE == ST_BB) {
-                        ra[2 * pts] = ar.d;
-                        ra[3 * pts] = ar.e;
-                        ra[4 * pts] = gog[a];
-                    }
-                    if (STAGE == ST_BBB) {
-                        ra[2 * pts] = ar.e * gogg[a] * gog[a];
-                        if (HAS_X2) ra[3 * pts] = ar.d * gog[a];
-                    }
-                }
-                if (ok) {
-#pragma unroll
-                    for (int c = 0; c < NCORN; ++c) {
-                        bool v = true;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a) v = v && (((c >> a) & 1) ? hi_ok[a] : lo_ok[a]);
-                        mask |= (v ? 1 : 0) << c;
-                    }
-                }
-            }
-            rec[0 * pts + i] = __int_as_float(base);
-            rec[1 * pts + i] = __int_as_float(mask);
+        for (int u = 0; u < PPL; ++u) {
+            const int i = u * 32 + lane;
+            if (i < PTS)
+                build_record<DIM, STAGE, HAS_U, HAS_X2, PTS>(recbuf + par * F4 * PTS, i, pin[u],
+                                                             pt0 + i < p.P, off, p, align);
         }
         __syncwarp();
+    };
+    // stream slices of one item -> xbuf[par]
+    auto issue_streams = [&](long long tl, int jj, int par) {
+        if (!HAS_X1 || jj >= V) return;
+        const int n = (int)(tl % p.N);
+        const long long qp0 = (tl / p.N) * PTS + 4 * q;
+        const int chan0 = jj * VEC;
+        float4* xb = xbuf + par * WS::XSLOTS * 32;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float* s1 = p.x1 + n * p.x1_sn + (long long)(chan0 + k) * p.x1_sc + qp0;
+            if (svec) {
+                cp_async16(xb + k * 32 + lane, s1, qp0 < p.P);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    cp_async4(reinterpret_cast<float*>(xb + k * 32 + lane) + t, s1 + t, qp0 + t < p.P);
+            }
+            if (HAS_X2) {
+                const float* s2 = p.x2 + n * p.x2_sn + (long long)(chan0 + k) * p.x2_sc + qp0;
+                if (svec) {
+                    cp_async16(xb + (VEC + k) * 32 + lane, s2, qp0 < p.P);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        cp_async4(reinterpret_cast<float*>(xb + (VEC + k) * 32 + lane) + t, s2 + t, qp0 + t < p.P);
+                }
+            }
+        }
+    };
+    // corner vectors of stage st of one item -> gbuf[st & 1]
+    auto issue_gathers = [&](long long tl, int jj, int rpar, int st) {
+        if (jj >= V || !(need_v || HAS_U)) return;
+        const int n = (int)(tl % p.N);
+        const float4* rec = recbuf + rpar * F4 * PTS;
+        const float* Vn = p.V + (long long)n * p.cell_stride + jj * VEC * p.chan_stride;
+        const float* Un = HAS_U ? p.U + (long long)n * p.cell_stride + jj * VEC * p.chan_stride : nullptr;
+        float4* gb = gbuf + (st & 1) * WS::GSLOTS * 32;
+#pragma unroll
+        for (int s = 0; s < PG; ++s) {
+            const float4 hd = rec[4 * q + st * PG + s];
+            const int base = __float_as_int(hd.x);
+            const int mask = __float_as_int(hd.y);
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c) {
+                const bool valid = (mask >> c) & 1;
+                const long long fo = (long long)(valid ? base + coff[c] : 0) * p.texel_stride;
+                if (VEC == 4) {
+                    if (need_v) cp_async16(gb + (s * NCORN + c) * 32 + lane, Vn + fo, valid);
+                    if (HAS_U) cp_async16(gb + ((PG + s) * NCORN + c) * 32 + lane, Un + fo, valid);
+                } else {
+                    if (need_v) cp_async4(gb + (s * NCORN + c) * 32 + lane, Vn + fo, valid);
+                    if (HAS_U) cp_async4(gb + ((PG + s) * NCORN + c) * 32 + lane, Un + fo, valid);
+                }
+            }
+        }
+    };
 
-        // ---------------- phase 2: L lanes per quad, VEC channels per lane ---
-        const long long qp0 = pt0 + 4 * q;          // first point of this lane's quad
-        const float* Vn = p.V + (long long)n * p.cell_stride;
-        const float* Un = HAS_U ? p.U + (long long)n * p.cell_stride : nullptr;
-        float* An = want_s ? p.acc + (long long)n * p.cell_stride : nullptr;
+    // ---- prologue: first item's records, streams and stage-0 gathers ------------------
+    load_inputs(tile);
+    phase1(tile, 0);
+    if (tile + tstep < total) load_inputs(tile + tstep);
+    issue_streams(tile, j, 0);
+    issue_gathers(tile, j, 0, 0);
+    cp_async_commit();
+
+    int tpar = 0;                                   // record buffer of the current tile
+    int ipar = 0;                                   // stream buffer of the current item
+    for (; tile < total; tile += tstep) {
+        const int n = (int)(tile % p.N);
+        const long long pt0 = (tile / p.N) * PTS;
+        const long long qp0 = pt0 + 4 * q;
+        const float4* rec = recbuf + tpar * F4 * PTS;
+        float* An = p.acc + (long long)n * p.cell_stride;
+        const bool next_tile = tile + tstep < total;
 
         float gg[4][DIM];
 #pragma unroll
@@ -339,153 +583,168 @@ cs_stage_kernel(const StageParams p) {
 #pragma unroll
             for (int a = 0; a < DIM; ++a) gg[t][a] = 0.f;
 
-        for (int jj = j; jj < V; jj += L) {
+        for (int it = 0; it < items_per_tile; ++it) {
+            const int jj = j + it * L;
+            const bool active = jj < V;
             const int chan0 = jj * VEC;
-            float x1[VEC][4], x2[VEC][4], y[VEC][4];
+            const bool last_item = (it + 1 == items_per_tile);
+            float x1[4][VEC], x2[4][VEC], y[4][VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                if (HAS_X1) stream_load4(x1[k], p.x1 + n * p.x1_sn + (long long)(chan0 + k) * p.x1_sc, qp0, p.P, svec);
-                if (HAS_X2) stream_load4(x2[k], p.x2 + n * p.x2_sn + (long long)(chan0 + k) * p.x2_sc, qp0, p.P, svec);
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) y[k][t] = 0.f;
-            }
-            const int foff = chan0 * p.chan_stride;
+                for (int k = 0; k < VEC; ++k) { x1[t][k] = 0.f; x2[t][k] = 0.f; y[t][k] = 0.f; }
 
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int ri = 4 * q + t;
-                const int base = __float_as_int(rec[0 * pts + ri]);
-                const int mask = __float_as_int(rec[1 * pts + ri]);
-                if (mask == 0) continue;
-                float w[DIM][2], dw[DIM][2], ew[DIM][2], gog[DIM], fx[DIM], hx[DIM];
+            for (int st = 0; st < NST; ++st) {
+                // ---- produce: next stage of this item, or stage 0 of the next item
+                if (st + 1 < NST) {
+                    issue_gathers(tile, jj, tpar, st + 1);
+                } else if (!last_item) {
+                    issue_streams(tile, jj + L, ipar ^ 1);
+                    issue_gathers(tile, jj + L, tpar, 0);
+                } else if (next_tile) {
+                    phase1(tile + tstep, tpar ^ 1);
+                    if (tile + 2 * tstep < total) load_inputs(tile + 2 * tstep);
+                    issue_streams(tile + tstep, j, ipar ^ 1);
+                    issue_gathers(tile + tstep, j, tpar ^ 1, 0);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();                 // everything but the group just committed has landed
+
+                // ---- consume stage st
+                if (st == 0 && HAS_X1 && active) {
+                    const float4* xb = xbuf + ipar * WS::XSLOTS * 32;
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const float* ra = rec + (2 + a * PA) * pts + ri;
-                    w[a][0] = ra[0];
-                    w[a][1] = ra[pts];
-                    if (STAGE == ST_B || STAGE == ST_BB) { dw[a][1] = ra[2 * pts]; dw[a][0] = -dw[a][1]; }
-                    if (STAGE == ST_BB) { ew[a][0] = ra[3 * pts]; ew[a][1] = -ew[a][0]; gog[a] = ra[4 * pts]; }
-                    if (STAGE == ST_BBB) {
-                        fx[a] = ra[2 * pts];                 // e * gogg * gog (low corner sign)
-                        if (HAS_X2) hx[a] = ra[3 * pts];     // d * gog        (high corner sign)
+                    for (int k = 0; k < VEC; ++k) {
+                        const float4 a4 = xb[k * 32 + lane];
+                        x1[0][k] = a4.x; x1[1][k] = a4.y; x1[2][k] = a4.z; x1[3][k] = a4.w;
+                        if (HAS_X2) {
+                            const float4 b4 = xb[(VEC + k) * 32 + lane];
+                            x2[0][k] = b4.x; x2[1][k] = b4.y; x2[2][k] = b4.z; x2[3][k] = b4.w;
+                        }
                     }
                 }
+                if (active) {
+                    const float4* gb = gbuf + (st & 1) * WS::GSLOTS * 32;
 #pragma unroll
-                for (int c = 0; c < NCORN; ++c) {
-                    if (!((mask >> c) & 1)) continue;
-                    int b[DIM];
-                    int texel = base;
+                    for (int s = 0; s < PG; ++s) {
+                        const int t = st * PG + s;
+                        const int ri = 4 * q + t;
+                        const float4 hd = rec[ri];
+                        const int base = __float_as_int(hd.x);
+                        const int mask = __float_as_int(hd.y);
+                        if (mask == 0) continue;
+                        float4 k0[CQ];
 #pragma unroll
-                    for (int a = 0; a < DIM; ++a) { b[a] = (c >> a) & 1; texel += b[a] * p.tstride[a]; }
-                    // products of the other axes' weights
-                    float wo[DIM];          // prod_{c != a} W_c
-                    float wall;             // prod_a W_a, in x,y,z order
-                    if (DIM == 2) {
-                        wo[0] = w[1][b[1]]; wo[1] = w[0][b[0]];
-                        wall = w[0][b[0]] * w[1][b[1]];
-                    } else {
-                        wo[0] = w[1][b[1]] * w[2][b[2]];
-                        wo[1] = w[0][b[0]] * w[2][b[2]];
-                        wo[2] = w[0][b[0]] * w[1][b[1]];
-                        wall = (w[0][b[0]] * w[1][b[1]]) * w[2][b[2]];
-                    }
-                    // stage coefficients for this (point, corner)
-                    float cy = 0.f;        // y      += V * cy
-                    float cu = 0.f;        // y      += U * cu
-                    float cs1 = 0.f;       // acc    += x1 * cs1
-                    float cs2 = 0.f;       // acc    += x2 * cs2
-                    float cg[DIM];         // gg[a]  += dot(V,x1) * cg[a]
-                    float cgu[DIM];        // gg[a]  += dot(U,x1) * cgu[a]
-                    if (STAGE == ST_F) {
-                        cy = wall;
-                    } else if (STAGE == ST_B) {
-                        cs1 = wall;
+                        for (int h = 0; h < CQ; ++h) k0[h] = rec[(1 + h) * PTS + ri];
+                        // gathered vectors of this point
+                        float vv[NCORN][VEC], uu[HAS_U ? NCORN : 1][VEC];
 #pragma unroll
-                        for (int a = 0; a < DIM; ++a) cg[a] = dw[a][b[a]] * wo[a];
-                    } else if (STAGE == ST_BB) {
-                        float A = 0.f;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a) A += dw[a][b[a]] * wo[a] * gog[a];
-                        cy = A; cs1 = A; cu = wall;
-                        if (DIM == 2) {
-                            // pure second derivatives only (cu2d:705-706)
-#pragma unroll
-                            for (int a = 0; a < DIM; ++a) cg[a] = ew[a][b[a]] * wo[a] * gog[a];
-                        } else {
-                            // full Hessian row + gOutInput term (cu3d:836-856)
-#pragma unroll
-                            for (int a = 0; a < DIM; ++a) {
-                                float s = ew[a][b[a]] * wo[a] * gog[a];
-#pragma unroll
-                                for (int bb = 0; bb < DIM; ++bb) {
-                                    if (bb == a) continue;
-                                    const int cc = 3 - a - bb;
-                                    s += dw[a][b[a]] * dw[bb][b[bb]] * w[cc][b[cc]] * gog[bb];
+                        for (int c = 0; c < NCORN; ++c) {
+                            if (VEC == 4) {
+                                if (need_v) {
+                                    const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
+                                    vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
                                 }
-                                cg[a] = s;
-                                cgu[a] = dw[a][b[a]] * wo[a];
+                                if (HAS_U) {
+                                    const float4 b4 = gb[((PG + s) * NCORN + c) * 32 + lane];
+                                    uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
+                                    uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
+                                }
+                            } else {
+                                if (need_v) vv[c][0] = gb[(s * NCORN + c) * 32 + lane].x;
+                                if (HAS_U) uu[HAS_U ? c : 0][0] = gb[((PG + s) * NCORN + c) * 32 + lane].x;
                             }
                         }
-                    } else {  // BBB: pure second derivatives (cu2d:876-885, cu3d:1054-1065)
-                        float E = 0.f, A = 0.f;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a) {
-                            E += (b[a] ? -fx[a] : fx[a]) * wo[a];
-                            if (HAS_X2) A += (b[a] ? hx[a] : -hx[a]) * wo[a];
-                        }
-                        cy = E; cs1 = E; cs2 = A;
-                    }
-
-                    const long long fo = (long long)texel * p.texel_stride + foff;
-                    FieldVec<VEC> vv, uu;
-                    if (need_v) {
-                        vv.load(Vn + fo, p.chan_stride);
                         if (want_y) {
 #pragma unroll
-                            for (int k = 0; k < VEC; ++k) y[k][t] = fmaf(vv.v[k], cy, y[k][t]);
+                            for (int c = 0; c < NCORN; ++c) {
+                                const float cy = f4get(k0[c >> 2], c & 3);
+#pragma unroll
+                                for (int k = 0; k < VEC; ++k) y[t][k] = fmaf(vv[c][k], cy, y[t][k]);
+                            }
+                            if (HAS_U) {
+#pragma unroll
+                                for (int h = 0; h < CQ; ++h) {
+                                    const float4 ku = rec[(1 + (1 + DIM) * CQ + h) * PTS + ri];
+#pragma unroll
+                                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                                        for (int k = 0; k < VEC; ++k)
+                                            y[t][k] = fmaf(uu[HAS_U ? 4 * h + cc : 0][k], f4get(ku, cc), y[t][k]);
+                                }
+                            }
                         }
-                    }
-                    if (HAS_U) {
-                        uu.load(Un + fo, p.chan_stride);
-                        if (want_y) {
+                        if (want_g) {
+                            float dot[NCORN];
 #pragma unroll
-                            for (int k = 0; k < VEC; ++k) y[k][t] = fmaf(uu.v[k], cu, y[k][t]);
+                            for (int c = 0; c < NCORN; ++c) {
+                                dot[c] = 0.f;
+#pragma unroll
+                                for (int k = 0; k < VEC; ++k) dot[c] = fmaf(vv[c][k], x1[t][k], dot[c]);
+                            }
+#pragma unroll
+                            for (int a = 0; a < DIM; ++a)
+#pragma unroll
+                                for (int h = 0; h < CQ; ++h) {
+                                    const float4 kg = rec[(1 + (1 + a) * CQ + h) * PTS + ri];
+#pragma unroll
+                                    for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                                }
+                            if (HAS_U && DIM == 3) {
+#pragma unroll
+                                for (int c = 0; c < NCORN; ++c) {
+                                    dot[c] = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < VEC; ++k) dot[c] = fmaf(uu[HAS_U ? c : 0][k], x1[t][k], dot[c]);
+                                }
+#pragma unroll
+                                for (int a = 0; a < DIM; ++a)
+#pragma unroll
+                                    for (int h = 0; h < CQ; ++h) {
+                                        const float4 kg = rec[(1 + (2 + DIM + a) * CQ + h) * PTS + ri];
+#pragma unroll
+                                        for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                                    }
+                            }
                         }
-                    }
-                    if (HAS_X1 && STAGE != ST_BBB && want_g) {
-                        float dot = 0.f;
+                        if (want_s) {
+                            float4 k1[CQ];
+                            if (HAS_X2) {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) dot = fmaf(vv.v[k], x1[k][t], dot);
+                                for (int h = 0; h < CQ; ++h) k1[h] = rec[(1 + CQ + h) * PTS + ri];
+                            }
 #pragma unroll
-                        for (int a = 0; a < DIM; ++a) gg[t][a] = fmaf(dot, cg[a], gg[t][a]);
-                        if (HAS_U && DIM == 3) {
-                            float du = 0.f;
+                            for (int c = 0; c < NCORN; ++c) {
+                                if ((mask >> c) & 1) {
+                                    const float cs1 = f4get(k0[c >> 2], c & 3);
+                                    float sv[VEC];
 #pragma unroll
-                            for (int k = 0; k < VEC; ++k) du = fmaf(uu.v[k], x1[k][t], du);
-#pragma unroll
-                            for (int a = 0; a < DIM; ++a) gg[t][a] = fmaf(du, cgu[a], gg[t][a]);
+                                    for (int k = 0; k < VEC; ++k) {
+                                        sv[k] = x1[t][k] * cs1;
+                                        if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1[c >> 2], c & 3), sv[k]);
+                                    }
+                                    FieldVec<VEC>::red(An + (long long)(base + coff[c]) * p.texel_stride
+                                                           + chan0 * p.chan_stride, sv);
+                                }
+                            }
                         }
-                    }
-                    if (HAS_X1 && want_s) {
-                        float s[VEC];
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) {
-                            s[k] = x1[k][t] * cs1;
-                            if (HAS_X2) s[k] = fmaf(x2[k][t], cs2, s[k]);
-                        }
-                        FieldVec<VEC>::red(An + fo, s);
                     }
                 }
             }
-            if (want_y) {
+            if (want_y && active) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    stream_store4(y[k], p.y + ((long long)n * p.C + chan0 + k) * p.P, qp0, p.P, svec);
+                for (int k = 0; k < VEC; ++k) {
+                    const float tmp[4] = {y[0][k], y[1][k], y[2][k], y[3][k]};
+                    stream_store4(tmp, p.y + ((long long)n * p.C + chan0 + k) * p.P, qp0, p.P, svec);
+                }
             }
+            ipar ^= 1;
         }
 
-        if ((STAGE == ST_B || STAGE == ST_BB) && want_g) {
+        if (want_g) {
             // sum the channel-partial gradients over the L lanes of the quad
+#pragma unroll
             for (int o = L >> 1; o > 0; o >>= 1) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
@@ -494,17 +753,26 @@ cs_stage_kernel(const StageParams p) {
             }
             if (j == 0) {
                 float* out = p.ggrid + ((long long)n * p.P + qp0) * DIM;
+                if (p.gvec4 && qp0 < p.P) {
+                    // 4 points x DIM floats, 16-byte aligned when P % 4 == 0
+                    const float* f = &gg[0][0];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (qp0 + t < p.P) {
+                    for (int v4 = 0; v4 < DIM; ++v4)
+                        reinterpret_cast<float4*>(out)[v4] = make_float4(f[4 * v4], f[4 * v4 + 1], f[4 * v4 + 2], f[4 * v4 + 3]);
+                } else {
 #pragma unroll
-                        for (int a = 0; a < DIM; ++a) out[t * DIM + a] = gg[t][a];
+                    for (int t = 0; t < 4; ++t) {
+                        if (qp0 + t < p.P) {
+#pragma unroll
+                            for (int a = 0; a < DIM; ++a) out[t * DIM + a] = gg[t][a];
+                        }
                     }
                 }
             }
         }
-        __syncwarp();
+        tpar ^= 1;
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace cs

@@ -29,8 +29,14 @@ def test_linear_no_multicell_equals_grid_sample(cuda, dim, shape, P):
     gshape = (N, 1, P, 2) if dim == 2 else (N, 1, 1, P, 3)
     grid = (torch.rand(gshape, generator=gen) * 2 - 1).to(cuda).requires_grad_(True)
     out = S.apply(inp, grid, "zeros", True, name, False)
-    ref = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
-    assert torch.equal(out, ref), "forward must be bit-identical to F.grid_sample"
+    # F.grid_sample hands 4-D bilinear/zeros/align_corners=True inputs to cuDNN when it can;
+    # ATen's own kernel (GridSampler.cu, the one the reference is derived from, cu2d:1-3)
+    # is what bit-equality is defined against.  The cuDNN result is checked with the tolerance.
+    with torch.backends.cudnn.flags(enabled=False):
+        ref = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert torch.equal(out, ref), "forward must be bit-identical to ATen's grid_sample kernel"
+    ref_cudnn = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert_close_scaled(out, ref_cudnn, "forward vs F.grid_sample (cuDNN path when taken)")
     gOut = torch.randn(ref.shape, generator=gen).to(cuda)
     gI, gG = torch.autograd.grad(out, [inp, grid], gOut)
     rI, rG = torch.autograd.grad(ref, [inp, grid], gOut)
@@ -46,7 +52,8 @@ def test_zero_padding_out_of_range_equals_grid_sample(cuda):
     inp = torch.rand(2, 8, 16, 16, generator=gen).to(cuda)
     grid = (torch.rand(2, 1, 4096, 2, generator=gen) * 3 - 1.5).to(cuda)
     out = S.apply(inp, grid, "zeros", True, "bilinear", False)
-    ref = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    with torch.backends.cudnn.flags(enabled=False):
+        ref = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
     assert torch.equal(out, ref)
     outb = S.apply(inp, grid, "border", True, "bilinear", False)
     refb = F.grid_sample(inp, grid, mode="bilinear", padding_mode="border", align_corners=True)
