@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=0, help="override the total number of points")
-    ap.add_argument("--cpu-sample", type=int, default=2 ** 15,
+    ap.add_argument("--cpu-sample", type=int, default=2 ** 19,
                     help="points per CPU-baseline step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -90,10 +90,12 @@ int run(const cs_problem* pb, cs::StageParams& p, int stage, bool has_u, bool ha
     const int vec = vec4 ? 4 : 1;
     // scalar fields: one lane walks all channels of its point quad (channel-first strides
     // give the lanes of a quad nothing to share)
-    int lanes = vec4 ? (pb->lanes ? pb->lanes : gcd8(p.C / 4)) : 1;
+    int lanes = vec4 ? gcd8(p.C / 4) : 1;
+    if (vec4 && pb->lanes && (p.C / 4) % pb->lanes == 0) lanes = pb->lanes;   // must divide C/4
     p.lshift = (lanes == 1) ? 0 : (lanes == 2) ? 1 : (lanes == 4) ? 2 : 3;
     const int pts = 128 >> p.lshift;
     p.num_ptiles = (p.P + pts - 1) / pts;
+    if (p.num_ptiles >= (1ll << 31)) return fail(CS_EUNSUPPORTED, "too many points per cell (%lld)", (long long)p.P);
     // stream vector width
     p.svec4 = (p.P % 4 == 0) && aligned16(p.x1) && aligned16(p.x2) && aligned16(p.y) &&
               p.x1_sn % 4 == 0 && p.x1_sc % 4 == 0 && p.x2_sn % 4 == 0 && p.x2_sc % 4 == 0;

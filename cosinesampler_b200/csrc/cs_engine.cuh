@@ -175,6 +175,10 @@ __device__ __forceinline__ void red_add_f32(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");
 }
 
+__device__ __forceinline__ float f4get(const float4& v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
 // 4 consecutive points of one channel of a [N,C,P] stream
 __device__ __forceinline__ void stream_load4(float (&v)[4], const float* base, long long p0,
                                              long long P, bool vec) {
@@ -184,8 +188,13 @@ __device__ __forceinline__ void stream_load4(float (&v)[4], const float* base, l
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         } else { v[0] = v[1] = v[2] = v[3] = 0.f; }
     } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (p0 + i < P) ? __ldcs(base + p0 + i) : 0.f;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const float x = (p0 + i < P) ? __ldcs(base + p0 + i) : 0.f;
+            if (i == 0) t.x = x; else if (i == 1) t.y = x; else if (i == 2) t.z = x; else t.w = x;
+        }
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 }
 __device__ __forceinline__ void stream_store4(const float (&v)[4], float* base, long long p0,
@@ -193,8 +202,11 @@ __device__ __forceinline__ void stream_store4(const float (&v)[4], float* base, 
     if (vec) {
         if (p0 < P) __stcs(reinterpret_cast<float4*>(base + p0), make_float4(v[0], v[1], v[2], v[3]));
     } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (p0 + i < P) __stcs(base + p0 + i, v[i]);
+        // ragged / unaligned streams: a real loop, so that the vector path above is not
+        // burdened with four predicated-off scalar stores
+        const float4 t = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) if (p0 + i < P) __stcs(base + p0 + i, f4get(t, i));
     }
 }
 
@@ -371,9 +383,6 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
                 make_float4(coef[k][4 * h], coef[k][4 * h + 1], coef[k][4 * h + 2], coef[k][4 * h + 3]);
 }
 
-__device__ __forceinline__ float f4get(const float4& v, int i) {
-    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
-}
 
 // ---------------------------------------------------------------------------
 // The stage kernel: a per-warp software pipeline
@@ -390,10 +399,10 @@ __device__ __forceinline__ float f4get(const float4& v, int i) {
 // the next tile (index map, sincospif, coefficients) also overlaps the gathers.
 // ---------------------------------------------------------------------------
 #ifndef CS_THREADS
-#define CS_THREADS 256
+#define CS_THREADS 128
 #endif
 #ifndef CS_MIN_BLOCKS
-#define CS_MIN_BLOCKS 1
+#define CS_MIN_BLOCKS 3
 #endif
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -419,12 +428,179 @@ template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2> stru
     static constexpr int PG = (DIM == 2) ? 2 : 1;            // points per stage
     static constexpr int NST = 4 / PG;
     static constexpr int GSLOTS = PG * NCORN * (HAS_U ? 2 : 1);   // gather slots per stage (V then U)
-    static constexpr int XSLOTS = (STAGE == ST_F) ? 0 : VEC * (HAS_X2 ? 2 : 1);   // stream slots per item
+    static constexpr int XSLOTS = 0;                         // streams are prefetched into registers
     static constexpr int REC = 2 * RL::FIELDS4 * PTS;        // records, double-buffered by tile
     static constexpr int GBUF = 2 * GSLOTS * 32;             // gathers, double-buffered by stage
     static constexpr int XBUF = 2 * XSLOTS * 32;             // streams, double-buffered by item
     static constexpr int TOTAL = REC + GBUF + XBUF;          // float4 per warp
 };
+
+// cp.async with a precomputed 32-bit shared address
+__device__ __forceinline__ void cp16(unsigned sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp16z(unsigned sdst, const void* gsrc, bool valid) {
+    const int n = valid ? 16 : 0;                       // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sdst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp4z(unsigned sdst, const void* gsrc, bool valid) {
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(sdst), "l"(gsrc), "r"(n) : "memory");
+}
+
+// Per-item constants a lane needs to issue and consume the stages of one work item.
+struct ItemCtx {
+    const char* vsrc;      // input field of cell n at this lane's channel vector (bytes)
+    const char* usrc;      // gOutInput field, same
+    char* adst;            // gInput accumulator, same
+    int tsb;               // texel stride in bytes
+};
+
+// Issue the corner gathers of stage `st` (PG points) of an item into gbuf[st & 1].
+template <int DIM, int VEC, int PG, int F4, int PTS, bool HAS_U, bool ALLV>
+__device__ __forceinline__ void issue_stage(const float4* rec, int q, int st, const ItemCtx& ic,
+                                            const int (&coff)[1 << DIM], unsigned gdst, bool need_v) {
+    constexpr int NCORN = 1 << DIM;
+    constexpr int GS = PG * NCORN * (HAS_U ? 2 : 1);
+    const unsigned d0 = gdst + (st & 1) * GS * 512;
+#pragma unroll
+    for (int s = 0; s < PG; ++s) {
+        const float4 hd = rec[4 * q + st * PG + s];
+        const int base = __float_as_int(hd.x);
+        const int mask = ALLV ? ((1 << NCORN) - 1) : __float_as_int(hd.y);
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) {
+            const bool valid = ALLV || ((mask >> c) & 1);
+            const long long fo = (long long)(valid ? base + coff[c] : 0) * ic.tsb;
+            if (VEC == 4) {
+                if (need_v) { if (ALLV) cp16(d0 + (s * NCORN + c) * 512, ic.vsrc + fo);
+                              else cp16z(d0 + (s * NCORN + c) * 512, ic.vsrc + fo, valid); }
+                if (HAS_U) { if (ALLV) cp16(d0 + ((PG + s) * NCORN + c) * 512, ic.usrc + fo);
+                             else cp16z(d0 + ((PG + s) * NCORN + c) * 512, ic.usrc + fo, valid); }
+            } else {
+                if (need_v) cp4z(d0 + (s * NCORN + c) * 512, ic.vsrc + fo, valid);
+                if (HAS_U) cp4z(d0 + ((PG + s) * NCORN + c) * 512, ic.usrc + fo, valid);
+            }
+        }
+    }
+}
+
+// Consume stage `st`: contract the gathered corner vectors of PG points.
+template <int DIM, int VEC, int STAGE, int PG, int PTS, bool HAS_U, bool HAS_X2, bool ALLV>
+__device__ __forceinline__ void consume_stage(const float4* rec, const float4* gb, int q, int lane, int st,
+                                              const ItemCtx& ic, const int (&coff)[1 << DIM],
+                                              bool want_y, bool want_g, bool want_s, bool need_v,
+                                              const float (&x1)[4][VEC], const float (&x2)[4][VEC],
+                                              float (&y)[4][VEC], float (&gg)[4][DIM]) {
+    using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
+    constexpr int NCORN = 1 << DIM;
+    constexpr int CQ = RL::CQ;
+#pragma unroll
+    for (int s = 0; s < PG; ++s) {
+        const int t = st * PG + s;
+        const int ri = 4 * q + t;
+        int base = 0, mask = (1 << NCORN) - 1;
+        if (!ALLV || want_s) {
+            const float4 hd = rec[ri];
+            base = __float_as_int(hd.x);
+            if (!ALLV) mask = __float_as_int(hd.y);
+        }
+        if (!ALLV && mask == 0) continue;
+        float4 k0[CQ];
+#pragma unroll
+        for (int h = 0; h < CQ; ++h) k0[h] = rec[(1 + h) * PTS + ri];
+        float vv[NCORN][VEC], uu[HAS_U ? NCORN : 1][VEC];
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) {
+            if (VEC == 4) {
+                if (need_v) {
+                    const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
+                    vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
+                }
+                if (HAS_U) {
+                    const float4 b4 = gb[((PG + s) * NCORN + c) * 32 + lane];
+                    uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
+                    uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
+                }
+            } else {
+                if (need_v) vv[c][0] = gb[(s * NCORN + c) * 32 + lane].x;
+                if (HAS_U) uu[HAS_U ? c : 0][0] = gb[((PG + s) * NCORN + c) * 32 + lane].x;
+            }
+        }
+        if (want_y) {
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c) {
+                const float cy = f4get(k0[c >> 2], c & 3);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) y[t][k] = fmaf(vv[c][k], cy, y[t][k]);
+            }
+            if (HAS_U) {
+#pragma unroll
+                for (int h = 0; h < CQ; ++h) {
+                    const float4 ku = rec[(1 + (1 + DIM) * CQ + h) * PTS + ri];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k)
+                            y[t][k] = fmaf(uu[HAS_U ? 4 * h + cc : 0][k], f4get(ku, cc), y[t][k]);
+                }
+            }
+        }
+        if (want_g) {
+            float dot[NCORN];
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c) {
+                dot[c] = 0.f;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) dot[c] = fmaf(vv[c][k], x1[t][k], dot[c]);
+            }
+#pragma unroll
+            for (int a = 0; a < DIM; ++a)
+#pragma unroll
+                for (int h = 0; h < CQ; ++h) {
+                    const float4 kg = rec[(1 + (1 + a) * CQ + h) * PTS + ri];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                }
+            if (HAS_U && DIM == 3) {
+#pragma unroll
+                for (int c = 0; c < NCORN; ++c) {
+                    dot[c] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) dot[c] = fmaf(uu[HAS_U ? c : 0][k], x1[t][k], dot[c]);
+                }
+#pragma unroll
+                for (int a = 0; a < DIM; ++a)
+#pragma unroll
+                    for (int h = 0; h < CQ; ++h) {
+                        const float4 kg = rec[(1 + (2 + DIM + a) * CQ + h) * PTS + ri];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                    }
+            }
+        }
+        if (want_s) {
+            float4 k1[CQ];
+            if (HAS_X2) {
+#pragma unroll
+                for (int h = 0; h < CQ; ++h) k1[h] = rec[(1 + CQ + h) * PTS + ri];
+            }
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c) {
+                if (ALLV || ((mask >> c) & 1)) {
+                    const float cs1 = f4get(k0[c >> 2], c & 3);
+                    float sv[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        sv[k] = x1[t][k] * cs1;
+                        if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1[c >> 2], c & 3), sv[k]);
+                    }
+                    FieldVec<VEC>::red(reinterpret_cast<float*>(ic.adst + (long long)(base + coff[c]) * ic.tsb), sv);
+                }
+            }
+        }
+    }
+}
 
 template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
 __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS)
@@ -432,7 +608,6 @@ cs_stage_kernel(const StageParams p) {
     using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
     using WS = WarpSmem<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
     constexpr int NCORN = 1 << DIM;
-    constexpr int CQ = RL::CQ;
     constexpr bool HAS_X1 = (STAGE != ST_F);
     constexpr int L = 1 << LSHIFT;                 // lanes per point quad
     constexpr int PTS = WS::PTS;                   // points per warp tile
@@ -440,6 +615,7 @@ cs_stage_kernel(const StageParams p) {
     constexpr int PG = WS::PG;
     constexpr int NST = WS::NST;
     constexpr int F4 = RL::FIELDS4;
+    constexpr int FULL = (1 << NCORN) - 1;
 
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31;
@@ -450,15 +626,18 @@ cs_stage_kernel(const StageParams p) {
     float4* wbase = smem4 + (size_t)warp * WS::TOTAL;
     float4* recbuf = wbase;                        // [2][F4][PTS]
     float4* gbuf = wbase + WS::REC;                // [2][GSLOTS][32]
-    float4* xbuf = gbuf + WS::GBUF;                // [2][XSLOTS][32]
+    const unsigned gdst = (unsigned)__cvta_generic_to_shared(gbuf + lane);
 
     const bool want_y = (p.y != nullptr);
     const bool want_g = (p.ggrid != nullptr) && (STAGE == ST_B || STAGE == ST_BB);
     const bool want_s = (p.acc != nullptr) && HAS_X1;
     const bool need_v = want_y || want_g;
     const bool svec = p.svec4 != 0;
-    const int V = p.C / VEC;                       // channel vectors per texel
-    const int njj = (V - j + L - 1) / L;           // items per tile for this lane (same for all lanes when L | V)
+    const int V = p.C / VEC;                       // channel vectors per texel; L divides V (API)
+    const int items_per_tile = V >> LSHIFT;
+    const int tsb = p.texel_stride * 4;
+    const int csb = p.chan_stride * 4 * VEC;       // bytes between channel vectors
+    const long long cellb = p.cell_stride * 4;
     // 2D forward always maps with align_corners = 1 (cu2d:307-308)
     const bool align = (STAGE == ST_F && DIM == 2) ? true : (p.align != 0);
 
@@ -474,108 +653,97 @@ cs_stage_kernel(const StageParams p) {
     const long long tstep = (long long)gridDim.x * wpb;
     long long tile = (long long)blockIdx.x * wpb + warp;
     if (tile >= total) return;
-    // all lanes of a warp must run the same number of items (warp-level syncs inside):
-    // lanes with no channel work (j >= V) still walk the pipeline with empty stages
-    const int items_per_tile = (V + L - 1) / L;
+    // (cell, point-tile) of a tile index, advanced incrementally: one 64-bit division per
+    // thread instead of several per tile
+    struct TileId { int n; int pt; };                // point-tile index fits 32 bits (API check)
+    const int step_n = (int)(tstep % p.N);
+    const int step_p = (int)(tstep / p.N);
+    auto advance = [&](TileId t) -> TileId {
+        t.n += step_n; t.pt += step_p;
+        if (t.n >= p.N) { t.n -= p.N; t.pt += 1; }
+        return t;
+    };
+    TileId tcur;
+    tcur.n = (int)(tile % p.N);
+    tcur.pt = (int)(tile / p.N);
+    TileId tnext = advance(tcur);
+    TileId tnext2 = advance(tnext);
 
     PointIn<DIM, STAGE> pin[PPL];
 
-    // ---- helpers ---------------------------------------------------------------------
-    auto load_inputs = [&](long long tl) {
-        const int n = (int)(tl % p.N);
-        const long long pt0 = (tl / p.N) * PTS;
+    auto load_inputs = [&](TileId t) {
+        const long long pt0 = (long long)t.pt * PTS;
 #pragma unroll
         for (int u = 0; u < PPL; ++u)
-            if (u * 32 + lane < PTS) load_point<DIM, STAGE>(pin[u], p, n, pt0 + u * 32 + lane);
+            if (u * 32 + lane < PTS) load_point<DIM, STAGE>(pin[u], p, t.n, pt0 + u * 32 + lane);
     };
-    auto phase1 = [&](long long tl, int par) {
-        const int n = (int)(tl % p.N);
-        const long long pt0 = (tl / p.N) * PTS;
-        const float off = __ldg(p.offset + n);
+    // phase 1 of a tile into record buffer `par`; returns "every corner of every point valid"
+    auto phase1 = [&](TileId t, int par) -> bool {
+        const long long pt0 = (long long)t.pt * PTS;
+        const float off = __ldg(p.offset + t.n);
         __syncwarp();                               // everyone is done reading this record buffer
+        bool allv = true;
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
             const int i = u * 32 + lane;
-            if (i < PTS)
-                build_record<DIM, STAGE, HAS_U, HAS_X2, PTS>(recbuf + par * F4 * PTS, i, pin[u],
-                                                             pt0 + i < p.P, off, p, align);
+            if (i < PTS) {
+                float4* rb = recbuf + par * F4 * PTS;
+                build_record<DIM, STAGE, HAS_U, HAS_X2, PTS>(rb, i, pin[u], pt0 + i < p.P, off, p, align);
+                allv = allv && (__float_as_int(rb[i].y) == FULL);
+            }
         }
-        __syncwarp();
+        return __all_sync(0xffffffffu, allv);       // also a warp barrier: records are visible
     };
-    // stream slices of one item -> xbuf[par]
-    auto issue_streams = [&](long long tl, int jj, int par) {
-        if (!HAS_X1 || jj >= V) return;
-        const int n = (int)(tl % p.N);
-        const long long qp0 = (tl / p.N) * PTS + 4 * q;
-        const int chan0 = jj * VEC;
-        float4* xb = xbuf + par * WS::XSLOTS * 32;
+    auto make_ctx = [&](TileId t, int jj) -> ItemCtx {
+        ItemCtx ic;
+        const long long o = (long long)t.n * cellb + (long long)jj * csb;
+        ic.vsrc = reinterpret_cast<const char*>(p.V) + o;
+        ic.usrc = reinterpret_cast<const char*>(p.U) + o;
+        ic.adst = reinterpret_cast<char*>(p.acc) + o;
+        ic.tsb = tsb;
+        return ic;
+    };
+    // Stream slices of the *next* item are prefetched straight into registers (plain coalesced
+    // 16-byte loads, one item ahead of their use); only the random corner gathers go through
+    // the shared-memory cp.async ring.
+    float4 xn1[VEC], xn2[HAS_X2 ? VEC : 1];
+    auto issue_streams = [&](TileId t, int it) {
+        if (!HAS_X1) return;
+        const long long qp0 = (long long)t.pt * PTS + 4 * q;
+        const int chan0 = (j + it * L) * VEC;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const float* s1 = p.x1 + n * p.x1_sn + (long long)(chan0 + k) * p.x1_sc + qp0;
-            if (svec) {
-                cp_async16(xb + k * 32 + lane, s1, qp0 < p.P);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    cp_async4(reinterpret_cast<float*>(xb + k * 32 + lane) + t, s1 + t, qp0 + t < p.P);
-            }
+            float tmp[4];
+            stream_load4(tmp, p.x1 + t.n * p.x1_sn + (long long)(chan0 + k) * p.x1_sc, qp0, p.P, svec);
+            xn1[k] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             if (HAS_X2) {
-                const float* s2 = p.x2 + n * p.x2_sn + (long long)(chan0 + k) * p.x2_sc + qp0;
-                if (svec) {
-                    cp_async16(xb + (VEC + k) * 32 + lane, s2, qp0 < p.P);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        cp_async4(reinterpret_cast<float*>(xb + (VEC + k) * 32 + lane) + t, s2 + t, qp0 + t < p.P);
-                }
+                stream_load4(tmp, p.x2 + t.n * p.x2_sn + (long long)(chan0 + k) * p.x2_sc, qp0, p.P, svec);
+                xn2[HAS_X2 ? k : 0] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
         }
     };
-    // corner vectors of stage st of one item -> gbuf[st & 1]
-    auto issue_gathers = [&](long long tl, int jj, int rpar, int st) {
-        if (jj >= V || !(need_v || HAS_U)) return;
-        const int n = (int)(tl % p.N);
-        const float4* rec = recbuf + rpar * F4 * PTS;
-        const float* Vn = p.V + (long long)n * p.cell_stride + jj * VEC * p.chan_stride;
-        const float* Un = HAS_U ? p.U + (long long)n * p.cell_stride + jj * VEC * p.chan_stride : nullptr;
-        float4* gb = gbuf + (st & 1) * WS::GSLOTS * 32;
-#pragma unroll
-        for (int s = 0; s < PG; ++s) {
-            const float4 hd = rec[4 * q + st * PG + s];
-            const int base = __float_as_int(hd.x);
-            const int mask = __float_as_int(hd.y);
-#pragma unroll
-            for (int c = 0; c < NCORN; ++c) {
-                const bool valid = (mask >> c) & 1;
-                const long long fo = (long long)(valid ? base + coff[c] : 0) * p.texel_stride;
-                if (VEC == 4) {
-                    if (need_v) cp_async16(gb + (s * NCORN + c) * 32 + lane, Vn + fo, valid);
-                    if (HAS_U) cp_async16(gb + ((PG + s) * NCORN + c) * 32 + lane, Un + fo, valid);
-                } else {
-                    if (need_v) cp_async4(gb + (s * NCORN + c) * 32 + lane, Vn + fo, valid);
-                    if (HAS_U) cp_async4(gb + ((PG + s) * NCORN + c) * 32 + lane, Un + fo, valid);
-                }
-            }
-        }
+    auto issue = [&](const float4* rec, int st, const ItemCtx& ic, bool allv) {
+        if (!(need_v || HAS_U)) return;
+        if (allv) issue_stage<DIM, VEC, PG, F4, PTS, HAS_U, true>(rec, q, st, ic, coff, gdst, need_v);
+        else issue_stage<DIM, VEC, PG, F4, PTS, HAS_U, false>(rec, q, st, ic, coff, gdst, need_v);
     };
 
     // ---- prologue: first item's records, streams and stage-0 gathers ------------------
-    load_inputs(tile);
-    phase1(tile, 0);
-    if (tile + tstep < total) load_inputs(tile + tstep);
-    issue_streams(tile, j, 0);
-    issue_gathers(tile, j, 0, 0);
+    load_inputs(tcur);
+    bool allv_cur = phase1(tcur, 0);
+    if (tile + tstep < total) load_inputs(tnext);
+    ItemCtx ic_cur = make_ctx(tcur, j);
+    issue_streams(tcur, 0);
+    issue(recbuf, 0, ic_cur, allv_cur);
     cp_async_commit();
 
     int tpar = 0;                                   // record buffer of the current tile
-    int ipar = 0;                                   // stream buffer of the current item
     for (; tile < total; tile += tstep) {
-        const int n = (int)(tile % p.N);
-        const long long pt0 = (tile / p.N) * PTS;
-        const long long qp0 = pt0 + 4 * q;
+        const int n = tcur.n;
+        const long long qp0 = (long long)tcur.pt * PTS + 4 * q;
         const float4* rec = recbuf + tpar * F4 * PTS;
-        float* An = p.acc + (long long)n * p.cell_stride;
         const bool next_tile = tile + tstep < total;
+        bool allv_next = true;
 
         float gg[4][DIM];
 #pragma unroll
@@ -585,161 +753,61 @@ cs_stage_kernel(const StageParams p) {
 
         for (int it = 0; it < items_per_tile; ++it) {
             const int jj = j + it * L;
-            const bool active = jj < V;
-            const int chan0 = jj * VEC;
             const bool last_item = (it + 1 == items_per_tile);
+            ItemCtx ic_next = ic_cur;
             float x1[4][VEC], x2[4][VEC], y[4][VEC];
 #pragma unroll
             for (int t = 0; t < 4; ++t)
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) { x1[t][k] = 0.f; x2[t][k] = 0.f; y[t][k] = 0.f; }
+            if (HAS_X1) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    x1[0][k] = xn1[k].x; x1[1][k] = xn1[k].y; x1[2][k] = xn1[k].z; x1[3][k] = xn1[k].w;
+                    if (HAS_X2) {
+                        x2[0][k] = xn2[HAS_X2 ? k : 0].x; x2[1][k] = xn2[HAS_X2 ? k : 0].y;
+                        x2[2][k] = xn2[HAS_X2 ? k : 0].z; x2[3][k] = xn2[HAS_X2 ? k : 0].w;
+                    }
+                }
+            }
 
 #pragma unroll
             for (int st = 0; st < NST; ++st) {
                 // ---- produce: next stage of this item, or stage 0 of the next item
                 if (st + 1 < NST) {
-                    issue_gathers(tile, jj, tpar, st + 1);
+                    issue(rec, st + 1, ic_cur, allv_cur);
                 } else if (!last_item) {
-                    issue_streams(tile, jj + L, ipar ^ 1);
-                    issue_gathers(tile, jj + L, tpar, 0);
+                    ic_next = make_ctx(tcur, jj + L);
+                    issue_streams(tcur, it + 1);
+                    issue(rec, 0, ic_next, allv_cur);
                 } else if (next_tile) {
-                    phase1(tile + tstep, tpar ^ 1);
-                    if (tile + 2 * tstep < total) load_inputs(tile + 2 * tstep);
-                    issue_streams(tile + tstep, j, ipar ^ 1);
-                    issue_gathers(tile + tstep, j, tpar ^ 1, 0);
+                    allv_next = phase1(tnext, tpar ^ 1);
+                    if (tile + 2 * tstep < total) load_inputs(tnext2);
+                    ic_next = make_ctx(tnext, j);
+                    issue_streams(tnext, 0);
+                    issue(recbuf + (tpar ^ 1) * F4 * PTS, 0, ic_next, allv_next);
                 }
                 cp_async_commit();
                 cp_async_wait<1>();                 // everything but the group just committed has landed
 
                 // ---- consume stage st
-                if (st == 0 && HAS_X1 && active) {
-                    const float4* xb = xbuf + ipar * WS::XSLOTS * 32;
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        const float4 a4 = xb[k * 32 + lane];
-                        x1[0][k] = a4.x; x1[1][k] = a4.y; x1[2][k] = a4.z; x1[3][k] = a4.w;
-                        if (HAS_X2) {
-                            const float4 b4 = xb[(VEC + k) * 32 + lane];
-                            x2[0][k] = b4.x; x2[1][k] = b4.y; x2[2][k] = b4.z; x2[3][k] = b4.w;
-                        }
-                    }
-                }
-                if (active) {
-                    const float4* gb = gbuf + (st & 1) * WS::GSLOTS * 32;
-#pragma unroll
-                    for (int s = 0; s < PG; ++s) {
-                        const int t = st * PG + s;
-                        const int ri = 4 * q + t;
-                        const float4 hd = rec[ri];
-                        const int base = __float_as_int(hd.x);
-                        const int mask = __float_as_int(hd.y);
-                        if (mask == 0) continue;
-                        float4 k0[CQ];
-#pragma unroll
-                        for (int h = 0; h < CQ; ++h) k0[h] = rec[(1 + h) * PTS + ri];
-                        // gathered vectors of this point
-                        float vv[NCORN][VEC], uu[HAS_U ? NCORN : 1][VEC];
-#pragma unroll
-                        for (int c = 0; c < NCORN; ++c) {
-                            if (VEC == 4) {
-                                if (need_v) {
-                                    const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
-                                    vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
-                                }
-                                if (HAS_U) {
-                                    const float4 b4 = gb[((PG + s) * NCORN + c) * 32 + lane];
-                                    uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
-                                    uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
-                                }
-                            } else {
-                                if (need_v) vv[c][0] = gb[(s * NCORN + c) * 32 + lane].x;
-                                if (HAS_U) uu[HAS_U ? c : 0][0] = gb[((PG + s) * NCORN + c) * 32 + lane].x;
-                            }
-                        }
-                        if (want_y) {
-#pragma unroll
-                            for (int c = 0; c < NCORN; ++c) {
-                                const float cy = f4get(k0[c >> 2], c & 3);
-#pragma unroll
-                                for (int k = 0; k < VEC; ++k) y[t][k] = fmaf(vv[c][k], cy, y[t][k]);
-                            }
-                            if (HAS_U) {
-#pragma unroll
-                                for (int h = 0; h < CQ; ++h) {
-                                    const float4 ku = rec[(1 + (1 + DIM) * CQ + h) * PTS + ri];
-#pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                                        for (int k = 0; k < VEC; ++k)
-                                            y[t][k] = fmaf(uu[HAS_U ? 4 * h + cc : 0][k], f4get(ku, cc), y[t][k]);
-                                }
-                            }
-                        }
-                        if (want_g) {
-                            float dot[NCORN];
-#pragma unroll
-                            for (int c = 0; c < NCORN; ++c) {
-                                dot[c] = 0.f;
-#pragma unroll
-                                for (int k = 0; k < VEC; ++k) dot[c] = fmaf(vv[c][k], x1[t][k], dot[c]);
-                            }
-#pragma unroll
-                            for (int a = 0; a < DIM; ++a)
-#pragma unroll
-                                for (int h = 0; h < CQ; ++h) {
-                                    const float4 kg = rec[(1 + (1 + a) * CQ + h) * PTS + ri];
-#pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
-                                }
-                            if (HAS_U && DIM == 3) {
-#pragma unroll
-                                for (int c = 0; c < NCORN; ++c) {
-                                    dot[c] = 0.f;
-#pragma unroll
-                                    for (int k = 0; k < VEC; ++k) dot[c] = fmaf(uu[HAS_U ? c : 0][k], x1[t][k], dot[c]);
-                                }
-#pragma unroll
-                                for (int a = 0; a < DIM; ++a)
-#pragma unroll
-                                    for (int h = 0; h < CQ; ++h) {
-                                        const float4 kg = rec[(1 + (2 + DIM + a) * CQ + h) * PTS + ri];
-#pragma unroll
-                                        for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
-                                    }
-                            }
-                        }
-                        if (want_s) {
-                            float4 k1[CQ];
-                            if (HAS_X2) {
-#pragma unroll
-                                for (int h = 0; h < CQ; ++h) k1[h] = rec[(1 + CQ + h) * PTS + ri];
-                            }
-#pragma unroll
-                            for (int c = 0; c < NCORN; ++c) {
-                                if ((mask >> c) & 1) {
-                                    const float cs1 = f4get(k0[c >> 2], c & 3);
-                                    float sv[VEC];
-#pragma unroll
-                                    for (int k = 0; k < VEC; ++k) {
-                                        sv[k] = x1[t][k] * cs1;
-                                        if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1[c >> 2], c & 3), sv[k]);
-                                    }
-                                    FieldVec<VEC>::red(An + (long long)(base + coff[c]) * p.texel_stride
-                                                           + chan0 * p.chan_stride, sv);
-                                }
-                            }
-                        }
-                    }
-                }
+                const float4* gb = gbuf + (st & 1) * WS::GSLOTS * 32;
+                if (allv_cur)
+                    consume_stage<DIM, VEC, STAGE, PG, PTS, HAS_U, HAS_X2, true>(
+                        rec, gb, q, lane, st, ic_cur, coff, want_y, want_g, want_s, need_v, x1, x2, y, gg);
+                else
+                    consume_stage<DIM, VEC, STAGE, PG, PTS, HAS_U, HAS_X2, false>(
+                        rec, gb, q, lane, st, ic_cur, coff, want_y, want_g, want_s, need_v, x1, x2, y, gg);
             }
-            if (want_y && active) {
+            if (want_y) {
+                const int chan0 = jj * VEC;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const float tmp[4] = {y[0][k], y[1][k], y[2][k], y[3][k]};
                     stream_store4(tmp, p.y + ((long long)n * p.C + chan0 + k) * p.P, qp0, p.P, svec);
                 }
             }
-            ipar ^= 1;
+            ic_cur = ic_next;
         }
 
         if (want_g) {
@@ -760,17 +828,20 @@ cs_stage_kernel(const StageParams p) {
                     for (int v4 = 0; v4 < DIM; ++v4)
                         reinterpret_cast<float4*>(out)[v4] = make_float4(f[4 * v4], f[4 * v4 + 1], f[4 * v4 + 2], f[4 * v4 + 3]);
                 } else {
+                    float flat[4 * DIM];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (qp0 + t < p.P) {
+                    for (int t = 0; t < 4; ++t)
 #pragma unroll
-                            for (int a = 0; a < DIM; ++a) out[t * DIM + a] = gg[t][a];
-                        }
-                    }
+                        for (int a = 0; a < DIM; ++a) flat[t * DIM + a] = gg[t][a];
+                    const int nvalid = (int)((p.P - qp0 < 4 ? (p.P - qp0 > 0 ? p.P - qp0 : 0) : 4)) * DIM;
+#pragma unroll
+                    for (int e = 0; e < 4 * DIM; ++e) if (e < nvalid) out[e] = flat[e];
                 }
             }
         }
         tpar ^= 1;
+        allv_cur = allv_next;
+        tcur = tnext; tnext = tnext2; tnext2 = advance(tnext2);
     }
     cp_async_wait<0>();
 }

@@ -17,19 +17,22 @@ from cosinesampler_b200 import ops  # noqa: E402
 from cosinesampler_b200.autograd import cell_offsets  # noqa: E402
 
 
-def timeit(fn, warm=3, iters=10):
+def timeit(fn, warm=3, iters=10, reps=5):
+    """Median over `reps` of (time of `iters` back-to-back calls) / iters: the queue stays full,
+    so host-side launch overhead does not leak into the device time of short kernels."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
-    for _ in range(iters):
+    for _ in range(reps):
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(iters):
+            fn()
         b.record()
         b.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / iters)
     return statistics.median(ts)
 
 
@@ -124,7 +127,7 @@ def main():
                                                                    kernel, True), pairs * (12 * d + 8 * C) + 2 * G),
             ]
             for stage, fn, nbytes in rcases:
-                rec(stage, timeit(fn, warm=2, iters=5), nbytes, "reference_cuda_op_sm100")
+                rec(stage, timeit(fn, warm=2, iters=5, reps=3), nbytes, "reference_cuda_op_sm100")
         del inp, grid, gOut, gOut2, gOG, gOgG, staged
         torch.cuda.empty_cache()
 
