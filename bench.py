@@ -41,6 +41,16 @@ CHAIN_BYTES_PER_PAIR = {"cfg5": 1544, "cfg3": 1544, "cfg4": 2432}
 CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tensors per step
 
 
+def ncu_traffic_bytes(label):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a stage kernel, from the committed
+    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg3_summary.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "ncu_stages_cfg3_summary.json")) as f:
+            return int(json.load(f)["kernels"][label]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -216,7 +226,10 @@ def run_ours(args):
     launches = _lib.launch_count() - n0
     ops.profiler = None
     clock_info = clocks.stop() if rank == 0 else None
-    loss_val = float(step_resident().item())
+    loss_t = step_resident().detach().clone()
+    if world > 1:
+        dist.all_reduce(loss_t)                      # each rank holds its share of the mean
+    loss_val = float(loss_t.item())
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -236,7 +249,7 @@ def run_ours(args):
     if top:
         a = stage[top]["bytes_per_launch"] / (stage[top]["ms_avg"] * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(a / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(a / peak, 4), "traffic": ncu_traffic_bytes(top), "peak_source": peak_src,
                     "launches": stage[top]["launches"], "ms_avg": round(stage[top]["ms_avg"], 4),
                     "bytes_per_launch": stage[top]["bytes_per_launch"],
                     "share_of_step": round(stage[top]["ms_total"] / ms, 4)}

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/cosine_sampler_b200.h"
 #include "cs_engine.cuh"
@@ -100,6 +101,14 @@ int run(const cs_problem* pb, cs::StageParams& p, int stage, bool has_u, bool ha
     p.svec4 = (p.P % 4 == 0) && aligned16(p.x1) && aligned16(p.x2) && aligned16(p.y) &&
               p.x1_sn % 4 == 0 && p.x1_sc % 4 == 0 && p.x2_sn % 4 == 0 && p.x2_sc % 4 == 0;
     p.gvec4 = (p.P % 4 == 0) && aligned16(p.ggrid);
+    {   // L2 working set of the grid-shaped fields this call touches at random: if all cells
+        // together exceed about half of the 126 MB L2, walk the cells one after the other
+        const bool reads_v = (p.V != nullptr) && (p.y != nullptr || p.ggrid != nullptr);
+        const int nfields = (reads_v ? 1 : 0) + (p.U ? 1 : 0) + (p.acc ? 1 : 0);
+        const long long footprint = (long long)nfields * p.N * p.cell_stride * 4;
+        static const long long limit_mb = [] { const char* e = getenv("CS_CELL_MAJOR_MB"); return e ? atoll(e) : 80ll; }();
+        p.cell_major = footprint > (limit_mb << 20);
+    }
     using Fn = cudaError_t (*)(int, bool, bool, const cs::StageParams&, cudaStream_t);
     static const Fn table[2][5] = {
         {cs::launch_d2_v4_l0, cs::launch_d2_v4_l1, cs::launch_d2_v4_l2, cs::launch_d2_v4_l3, cs::launch_d2_v1_l0},

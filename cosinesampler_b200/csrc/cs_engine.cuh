@@ -51,6 +51,8 @@ struct StageParams {
     long long P;
     long long num_ptiles;  // tiles per cell
     int lshift;          // log2(lanes per quad)
+    int cell_major;      // tile order: 1 = all point tiles of cell 0, then cell 1, ... (bounds the L2 working set
+                         // to one cell's fields); 0 = cell index fastest (cells of a point run together)
     // grid-shaped fields (same layout for V, U, acc)
     long long cell_stride;  // elements between cells
     int texel_stride;       // elements between texels (C channel-last, 1 channel-first)
@@ -404,6 +406,15 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
 #ifndef CS_MIN_BLOCKS
 #define CS_MIN_BLOCKS 3
 #endif
+#ifndef CS_MIN_BLOCKS_3D
+#define CS_MIN_BLOCKS_3D 2
+#endif
+#ifndef CS_PG2
+#define CS_PG2 2
+#endif
+#ifndef CS_PG3
+#define CS_PG3 1
+#endif
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -425,7 +436,7 @@ template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2> stru
     using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
     static constexpr int NCORN = 1 << DIM;
     static constexpr int PTS = 128 >> LSHIFT;
-    static constexpr int PG = (DIM == 2) ? 2 : 1;            // points per stage
+    static constexpr int PG = (DIM == 2) ? CS_PG2 : CS_PG3;  // points per stage
     static constexpr int NST = 4 / PG;
     static constexpr int GSLOTS = PG * NCORN * (HAS_U ? 2 : 1);   // gather slots per stage (V then U)
     static constexpr int XSLOTS = 0;                         // streams are prefetched into registers
@@ -603,7 +614,7 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
 }
 
 template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
-__global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS)
+__global__ void __launch_bounds__(CS_THREADS, (DIM == 2 ? CS_MIN_BLOCKS : CS_MIN_BLOCKS_3D))
 cs_stage_kernel(const StageParams p) {
     using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
     using WS = WarpSmem<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
@@ -656,16 +667,19 @@ cs_stage_kernel(const StageParams p) {
     // (cell, point-tile) of a tile index, advanced incrementally: one 64-bit division per
     // thread instead of several per tile
     struct TileId { int n; int pt; };                // point-tile index fits 32 bits (API check)
-    const int step_n = (int)(tstep % p.N);
-    const int step_p = (int)(tstep / p.N);
+    const bool cell_major = p.cell_major != 0;
+    const int nptiles = (int)p.num_ptiles;
+    const int step_n = cell_major ? (int)(tstep / nptiles) : (int)(tstep % p.N);
+    const int step_p = cell_major ? (int)(tstep % nptiles) : (int)(tstep / p.N);
     auto advance = [&](TileId t) -> TileId {
         t.n += step_n; t.pt += step_p;
-        if (t.n >= p.N) { t.n -= p.N; t.pt += 1; }
+        if (cell_major) { if (t.pt >= nptiles) { t.pt -= nptiles; t.n += 1; } }
+        else { if (t.n >= p.N) { t.n -= p.N; t.pt += 1; } }
         return t;
     };
     TileId tcur;
-    tcur.n = (int)(tile % p.N);
-    tcur.pt = (int)(tile / p.N);
+    tcur.n = cell_major ? (int)(tile / nptiles) : (int)(tile % p.N);
+    tcur.pt = cell_major ? (int)(tile % nptiles) : (int)(tile / p.N);
     TileId tnext = advance(tcur);
     TileId tnext2 = advance(tnext);
 
