@@ -52,7 +52,9 @@ def main():
             ref_mods[d] = build_ref.load("_cosine_%dd" % d)
     except Exception as e:
         print(json.dumps({"note": "reference op unavailable: %s" % e}))
-    configs = [("cfg3", 2, (4, 16, 256, 256), 2 ** 20, 0), ("cfg4", 3, (4, 16, 64, 64, 64), 2 ** 22, 2)]
+    configs = [("cfg3", 2, (4, 16, 256, 256), 2 ** 20, 0), ("cfg4", 3, (4, 16, 64, 64, 64), 2 ** 22, 2),
+               # the shapes of the reference's own scripts (test_2d.py:26-38, test_3d.py:19-32)
+               ("pixel2d", 2, (96, 4, 16, 16), 100000, 0), ("pixel3d", 3, (50, 4, 16, 16, 16), 100000, 0)]
     if len(sys.argv) > 1:
         configs = [c for c in configs if c[0] in sys.argv[1:]]
     for name, dim, shape, P, kernel in configs:
