@@ -58,6 +58,7 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
     if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
     if (pb->field_layout < 0 || pb->field_layout > 1) return fail(CS_EINVAL, "bad field_layout %d", pb->field_layout);
+    if (pb->small_cell < 0 || pb->small_cell > 2) return fail(CS_EINVAL, "bad small_cell %d", pb->small_cell);
     if (pb->lanes != 0 && pb->lanes != 1 && pb->lanes != 2 && pb->lanes != 4 && pb->lanes != 8)
         return fail(CS_EINVAL, "lanes must be 0,1,2,4 or 8");
     if (pb->N == 0 || pb->C == 0 || pb->P == 0) return CS_NOTHING_TO_DO;   // empty problem (cu2d:904)
@@ -76,6 +77,7 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     p.grid_vec2 = ((reinterpret_cast<uintptr_t>(grid) & 7u) == 0) && (pb->grid_stride_n % 2 == 0);
     p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
     p.multicell = pb->multicell; p.index_mode = pb->index_mode;
+    p.small_cell = pb->small_cell;
     return 0;
 }
 

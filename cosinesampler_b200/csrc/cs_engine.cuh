@@ -51,6 +51,7 @@ struct StageParams {
     long long P;
     long long num_ptiles;  // tiles per cell
     int lshift;          // log2(lanes per quad)
+    int small_cell;      // 0 auto, 1 never, 2 whenever it fits: shared-memory small-cell kernel
     int cell_major;      // tile order: 1 = all point tiles of cell 0, then cell 1, ... (bounds the L2 working set
                          // to one cell's fields); 0 = cell index fastest (cells of a point run together)
     // grid-shaped fields (same layout for V, U, acc)
@@ -497,7 +498,9 @@ __device__ __forceinline__ void issue_stage(const float4* rec, int q, int st, co
 }
 
 // Consume stage `st`: contract the gathered corner vectors of PG points.
-template <int DIM, int VEC, int STAGE, int PG, int PTS, bool HAS_U, bool HAS_X2, bool ALLV>
+// SMEMF: the fields (V, U, accumulator) of the cell live in shared memory (small-cell kernel):
+// corner vectors are read straight from there and the scatter uses shared-memory atomics.
+template <int DIM, int VEC, int STAGE, int PG, int PTS, bool HAS_U, bool HAS_X2, bool ALLV, bool SMEMF = false>
 __device__ __forceinline__ void consume_stage(const float4* rec, const float4* gb, int q, int lane, int st,
                                               const ItemCtx& ic, const int (&coff)[1 << DIM],
                                               bool want_y, bool want_g, bool want_s, bool need_v,
@@ -511,7 +514,7 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
         const int t = st * PG + s;
         const int ri = 4 * q + t;
         int base = 0, mask = (1 << NCORN) - 1;
-        if (!ALLV || want_s) {
+        if (!ALLV || want_s || SMEMF) {
             const float4 hd = rec[ri];
             base = __float_as_int(hd.x);
             if (!ALLV) mask = __float_as_int(hd.y);
@@ -523,7 +526,28 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
         float vv[NCORN][VEC], uu[HAS_U ? NCORN : 1][VEC];
 #pragma unroll
         for (int c = 0; c < NCORN; ++c) {
-            if (VEC == 4) {
+            if (SMEMF) {
+                const bool valid = ALLV || ((mask >> c) & 1);
+                const long long fo = (long long)(valid ? base + coff[c] : 0) * ic.tsb;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { vv[c][k] = 0.f; if (HAS_U) uu[HAS_U ? c : 0][k] = 0.f; }
+                if (valid) {
+                    if (VEC == 4) {
+                        if (need_v) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(ic.vsrc + fo);
+                            vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
+                        }
+                        if (HAS_U) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(ic.usrc + fo);
+                            uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
+                            uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
+                        }
+                    } else {
+                        if (need_v) vv[c][0] = *reinterpret_cast<const float*>(ic.vsrc + fo);
+                        if (HAS_U) uu[HAS_U ? c : 0][0] = *reinterpret_cast<const float*>(ic.usrc + fo);
+                    }
+                }
+            } else if (VEC == 4) {
                 if (need_v) {
                     const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
                     vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
@@ -606,7 +630,13 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
                         sv[k] = x1[t][k] * cs1;
                         if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1[c >> 2], c & 3), sv[k]);
                     }
-                    FieldVec<VEC>::red(reinterpret_cast<float*>(ic.adst + (long long)(base + coff[c]) * ic.tsb), sv);
+                    float* dst = reinterpret_cast<float*>(ic.adst + (long long)(base + coff[c]) * ic.tsb);
+                    if (SMEMF) {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) atomicAdd(dst + k, sv[k]);    // red.shared.add.f32
+                    } else {
+                        FieldVec<VEC>::red(dst, sv);
+                    }
                 }
             }
         }
@@ -858,6 +888,188 @@ cs_stage_kernel(const StageParams p) {
         tcur = tnext; tnext = tnext2; tnext2 = advance(tnext2);
     }
     cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------
+// Small-cell kernel: when one cell's fields fit in shared memory (the shapes of
+// the reference's own scripts, e.g. [96,4,16,16] = 4 KiB per cell, test_2d.py:26)
+// a block stages the cell once, gathers from shared memory and accumulates the
+// scatter in a shared-memory private copy that is flushed with one vector red
+// per 16 bytes at the end -- the "shared-memory-privatised accumulation when the
+// grid fits" of the north star.  Many points fall on few texels here, so the
+// global-atomic version serialises in L2; the private copy does not.
+//
+// grid = (splits, N): block (s, n) handles point tiles s, s+splits, ... of cell n,
+// its warps taking them round-robin.
+// ---------------------------------------------------------------------------
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
+__global__ void __launch_bounds__(256)
+cs_small_kernel(const StageParams p) {
+    using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
+    constexpr int NCORN = 1 << DIM;
+    constexpr bool HAS_X1 = (STAGE != ST_F);
+    constexpr int L = 1 << LSHIFT;
+    constexpr int PTS = 128 >> LSHIFT;
+    constexpr int PPL = (PTS + 31) / 32;
+    constexpr int F4 = RL::FIELDS4;
+    constexpr int FULL = (1 << NCORN) - 1;
+
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int q = lane >> LSHIFT;
+    const int j = lane & (L - 1);
+    const int n = blockIdx.y;
+
+    const bool want_y = (p.y != nullptr);
+    const bool want_g = (p.ggrid != nullptr) && (STAGE == ST_B || STAGE == ST_BB);
+    const bool want_s = (p.acc != nullptr) && HAS_X1;
+    const bool need_v = want_y || want_g;
+    const bool svec = p.svec4 != 0;
+    const int V = p.C / VEC;
+    const int items_per_tile = V >> LSHIFT;
+    const int tsb = p.texel_stride * 4;
+    const int csb = p.chan_stride * 4 * VEC;
+    const bool align = (STAGE == ST_F && DIM == 2) ? true : (p.align != 0);
+    const int cell_f4 = (int)(p.cell_stride / 4);          // cell size in float4 (cell elements % 4 == 0, API)
+
+    // shared memory: [V][U][acc] fields of the cell, then one record buffer per warp
+    float4* sV = smem4;
+    float4* sU = sV + (need_v ? cell_f4 : 0);
+    float4* sA = sU + (HAS_U ? cell_f4 : 0);
+    float4* recs = sA + (want_s ? cell_f4 : 0);
+    float4* rec4 = recs + (size_t)warp * F4 * PTS;
+
+    {
+        const float4* gV = reinterpret_cast<const float4*>(p.V + (long long)n * p.cell_stride);
+        const float4* gU = reinterpret_cast<const float4*>(p.U + (long long)n * p.cell_stride);
+        for (int i = threadIdx.x; i < cell_f4; i += blockDim.x) {
+            if (need_v) sV[i] = __ldg(gV + i);
+            if (HAS_U) sU[i] = __ldg(gU + i);
+            if (want_s) sA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+
+    int coff[NCORN];
+#pragma unroll
+    for (int c = 0; c < NCORN; ++c) {
+        coff[c] = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) coff[c] += ((c >> a) & 1) * p.tstride[a];
+    }
+    const float off = __ldg(p.offset + n);
+
+    for (long long pt = (long long)blockIdx.x * wpb + warp; pt < p.num_ptiles; pt += (long long)gridDim.x * wpb) {
+        const long long pt0 = pt * PTS;
+        const long long qp0 = pt0 + 4 * q;
+        PointIn<DIM, STAGE> pin[PPL];
+#pragma unroll
+        for (int u = 0; u < PPL; ++u)
+            if (u * 32 + lane < PTS) load_point<DIM, STAGE>(pin[u], p, n, pt0 + u * 32 + lane);
+
+        // stream slices of the first item: issued before phase 1 so their latency overlaps it
+        float x1[4][VEC], x2[4][VEC], y[4][VEC];
+        auto load_streams = [&](int it) {
+            const int chan0 = (j + it * L) * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                if (HAS_X1) stream_load4(tmp, p.x1 + n * p.x1_sn + (long long)(chan0 + k) * p.x1_sc, qp0, p.P, svec);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x1[t][k] = tmp[t];
+                if (HAS_X2) stream_load4(tmp, p.x2 + n * p.x2_sn + (long long)(chan0 + k) * p.x2_sc, qp0, p.P, svec);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x2[t][k] = HAS_X2 ? tmp[t] : 0.f;
+            }
+        };
+        load_streams(0);
+
+        __syncwarp();                                   // previous tile's records are no longer read
+        bool allv = true;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int i = u * 32 + lane;
+            if (i < PTS) {
+                build_record<DIM, STAGE, HAS_U, HAS_X2, PTS>(rec4, i, pin[u], pt0 + i < p.P, off, p, align);
+                allv = allv && (__float_as_int(rec4[i].y) == FULL);
+            }
+        }
+        allv = __all_sync(0xffffffffu, allv);
+
+        float gg[4][DIM];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) gg[t][a] = 0.f;
+
+        for (int it = 0; it < items_per_tile; ++it) {
+            const int jj = j + it * L;
+            if (it > 0) load_streams(it);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) y[t][k] = 0.f;
+            ItemCtx ic;
+            ic.vsrc = reinterpret_cast<const char*>(sV) + (long long)jj * csb;
+            ic.usrc = reinterpret_cast<const char*>(sU) + (long long)jj * csb;
+            ic.adst = reinterpret_cast<char*>(sA) + (long long)jj * csb;
+            ic.tsb = tsb;
+            if (allv)
+                consume_stage<DIM, VEC, STAGE, 4, PTS, HAS_U, HAS_X2, true, true>(
+                    rec4, nullptr, q, lane, 0, ic, coff, want_y, want_g, want_s, need_v, x1, x2, y, gg);
+            else
+                consume_stage<DIM, VEC, STAGE, 4, PTS, HAS_U, HAS_X2, false, true>(
+                    rec4, nullptr, q, lane, 0, ic, coff, want_y, want_g, want_s, need_v, x1, x2, y, gg);
+            if (want_y) {
+                const int chan0 = jj * VEC;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float tmp[4] = {y[0][k], y[1][k], y[2][k], y[3][k]};
+                    stream_store4(tmp, p.y + ((long long)n * p.C + chan0 + k) * p.P, qp0, p.P, svec);
+                }
+            }
+        }
+
+        if (want_g) {
+#pragma unroll
+            for (int o = L >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) gg[t][a] += __shfl_xor_sync(0xffffffffu, gg[t][a], o);
+            }
+            if (j == 0) {
+                float* out = p.ggrid + ((long long)n * p.P + qp0) * DIM;
+                if (p.gvec4 && qp0 < p.P) {
+                    const float* f = &gg[0][0];
+#pragma unroll
+                    for (int v4 = 0; v4 < DIM; ++v4)
+                        reinterpret_cast<float4*>(out)[v4] = make_float4(f[4 * v4], f[4 * v4 + 1], f[4 * v4 + 2], f[4 * v4 + 3]);
+                } else {
+                    float flat[4 * DIM];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int a = 0; a < DIM; ++a) flat[t * DIM + a] = gg[t][a];
+                    const int nvalid = (int)((p.P - qp0 < 4 ? (p.P - qp0 > 0 ? p.P - qp0 : 0) : 4)) * DIM;
+#pragma unroll
+                    for (int e = 0; e < 4 * DIM; ++e) if (e < nvalid) out[e] = flat[e];
+                }
+            }
+        }
+    }
+
+    if (want_s) {
+        // flush the private accumulator: one 16-byte vector red per float4, coalesced
+        __syncthreads();
+        float* gA = p.acc + (long long)n * p.cell_stride;
+        for (int i = threadIdx.x; i < cell_f4; i += blockDim.x) {
+            const float4 v = sA[i];
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(gA + 4 * i, v.x, v.y, v.z, v.w);
+        }
+    }
 }
 
 }  // namespace cs

@@ -63,6 +63,17 @@ def get_index_mode():
     return "fused" if _INDEX_MODE == _lib.INDEX_FUSED else "separate"
 
 
+_SMALL_CELL = {"auto": 0, "never": 1, "always": 2}[os.environ.get("COSINE_SAMPLER_SMALL_CELL", "auto")]
+
+
+def set_small_cell(mode):
+    """'auto' (default): cells whose fields fit in shared memory take the shared-memory kernel
+    (gathers from shared memory, privatised scatter); 'never' / 'always' force the choice
+    ('always' still falls back when the cell does not fit)."""
+    global _SMALL_CELL
+    _SMALL_CELL = {"auto": 0, "never": 1, "always": 2}[mode]
+
+
 def set_lanes(lanes):
     """0 = automatic; 1/2/4/8 lanes per point quad (1 = whole channel loop in one thread)."""
     global _LANES
@@ -236,6 +247,7 @@ def _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multice
     pb.field_layout = layout
     pb.grid_stride_n = grid_sn
     pb.lanes = _LANES
+    pb.small_cell = _SMALL_CELL
     return pb
 
 

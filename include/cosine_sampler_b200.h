@@ -75,7 +75,8 @@ typedef struct cs_problem {
     int32_t field_layout;  /* CS_LAYOUT_* of input, gOutInput and gInput in this call */
     int64_t grid_stride_n; /* elements between cells of `grid`; P*dim if contiguous, 0 if expanded */
     int32_t lanes;         /* 0 = auto; else 1,2,4,8 lanes cooperating on one point quad */
-    int32_t reserved;
+    int32_t small_cell;    /* 0 = auto: cells whose fields fit in shared memory take the shared-memory
+                              kernel; 1 = never; 2 = whenever it fits */
 } cs_problem;
 
 /* Strided view of a [N, C, P] point stream whose P axis is contiguous.

@@ -40,9 +40,10 @@ def _offset(N, multicell):
 
 
 def _run_all(cuda, dim, N, C, P, kernel, multicell, pad=0, align=True, seed=0, lo=-1.0, hi=1.0,
-             sizes=None, index_mode="separate"):
+             sizes=None, index_mode="separate", small_cell="auto"):
     from cosinesampler_b200 import ops
     ops.set_index_mode(index_mode)
+    ops.set_small_cell(small_cell)
     im = 0 if index_mode == "separate" else 1
     inp, grid, gOut, gOG, gOgG, gOI, gOggO = _inputs(dim, N, C, P, seed, lo, hi, sizes)
     off = _offset(N, multicell)
@@ -90,21 +91,29 @@ def _run_all(cuda, dim, N, C, P, kernel, multicell, pad=0, align=True, seed=0, l
         assert_close_scaled(fused[1], ref3[1], "BBB fused ggOut")
     finally:
         ops.set_index_mode("separate")
+        ops.set_small_cell("auto")
 
 
+# both kernels of the library: the cp.async-pipelined global-memory kernel ("never") and the
+# shared-memory small-cell kernel with privatised scatter ("always")
+PATHS = ["never", "always"]
+
+
+@pytest.mark.parametrize("small_cell", PATHS)
 @pytest.mark.parametrize("multicell", [True, False])
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("dim", [2, 3])
-def test_all_stages_channel_last_c16(cuda, dim, kernel, multicell):
-    _run_all(cuda, dim, N=3, C=16, P=1000, kernel=kernel, multicell=multicell)
+def test_all_stages_channel_last_c16(cuda, dim, kernel, multicell, small_cell):
+    _run_all(cuda, dim, N=3, C=16, P=1000, kernel=kernel, multicell=multicell, small_cell=small_cell)
 
 
+@pytest.mark.parametrize("small_cell", PATHS)
 @pytest.mark.parametrize("C,P", [(4, 257), (8, 512), (32, 130), (12, 64), (6, 100), (1, 33), (64, 40), (20, 7)])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_channel_counts_and_ragged_point_counts(cuda, dim, C, P):
+def test_channel_counts_and_ragged_point_counts(cuda, dim, C, P, small_cell):
     """C % 4 == 0 takes the channel-last vector path with 1/2/4/8 lanes per quad; other C the
     scalar channel-first path; P % 4 != 0 the scalar stream path; tiles end ragged."""
-    _run_all(cuda, dim, N=2, C=C, P=P, kernel=0, multicell=True, seed=C * 1000 + P)
+    _run_all(cuda, dim, N=2, C=C, P=P, kernel=0, multicell=True, seed=C * 1000 + P, small_cell=small_cell)
 
 
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8])
@@ -118,15 +127,24 @@ def test_lane_override(cuda, lanes):
         ops.set_lanes(0)
 
 
+@pytest.mark.parametrize("small_cell", PATHS)
 @pytest.mark.parametrize("align", [True, False])
 @pytest.mark.parametrize("pad", [0, 1, 2])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_padding_modes_and_align_corners_out_of_range_points(cuda, dim, pad, align):
+def test_padding_modes_and_align_corners_out_of_range_points(cuda, dim, pad, align, small_cell):
     """coordinates in [-1.4, 1.4]: zeros padding drops out-of-range corners, border clips,
     reflection reflects (over [0,S-2] when align_corners, cu2d:184-188)."""
     for kernel, multicell in itertools.product((0, 2, 1), (True, False)):
         _run_all(cuda, dim, N=2, C=8, P=400, kernel=kernel, multicell=multicell, pad=pad, align=align,
-                 lo=-1.4, hi=1.4, seed=17 + pad)
+                 lo=-1.4, hi=1.4, seed=17 + pad, small_cell=small_cell)
+
+
+def test_contended_scatter_on_a_tiny_cell(cuda):
+    """The reference's own shapes (test_2d.py:26-38): many points on 16x16 cells, so thousands of
+    contributions land on each texel; both scatter paths must agree with the oracle."""
+    for path in PATHS:
+        _run_all(cuda, 2, N=6, C=4, P=20000, kernel=0, multicell=True, sizes=(16, 16), seed=3, small_cell=path)
+        _run_all(cuda, 3, N=3, C=4, P=20000, kernel=0, multicell=True, sizes=(8, 8, 8), seed=4, small_cell=path)
 
 
 def test_fused_index_mode(cuda):
