@@ -13,6 +13,6 @@ _lib.load()  # fail loudly, at import time, when the native library is missing
 
 from .modules_2d import CosineSampler2d  # noqa: E402
 from .modules_3d import CosineSampler3d  # noqa: E402
-from .ops import set_index_mode, get_index_mode, set_lanes, set_small_cell  # noqa: E402
+from .ops import set_index_mode, get_index_mode, set_lanes, set_small_cell, set_grad_order  # noqa: E402
 
-__all__ = ["CosineSampler2d", "CosineSampler3d", "set_index_mode", "get_index_mode", "set_lanes", "set_small_cell"]
+__all__ = ["CosineSampler2d", "CosineSampler3d", "set_index_mode", "get_index_mode", "set_lanes", "set_small_cell", "set_grad_order"]

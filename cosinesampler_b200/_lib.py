@@ -33,6 +33,7 @@ class Problem(ctypes.Structure):
         ("index_mode", ctypes.c_int32), ("field_layout", ctypes.c_int32),
         ("grid_stride_n", ctypes.c_int64),
         ("lanes", ctypes.c_int32), ("small_cell", ctypes.c_int32),
+        ("grad_order", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 

@@ -58,6 +58,7 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
     if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
     if (pb->field_layout < 0 || pb->field_layout > 1) return fail(CS_EINVAL, "bad field_layout %d", pb->field_layout);
+    if (pb->grad_order < 0 || pb->grad_order > 1) return fail(CS_EINVAL, "bad grad_order %d", pb->grad_order);
     if (pb->small_cell < 0 || pb->small_cell > 2) return fail(CS_EINVAL, "bad small_cell %d", pb->small_cell);
     if (pb->lanes != 0 && pb->lanes != 1 && pb->lanes != 2 && pb->lanes != 4 && pb->lanes != 8)
         return fail(CS_EINVAL, "lanes must be 0,1,2,4 or 8");
@@ -163,6 +164,83 @@ __global__ void __launch_bounds__(256) cs_layout_kernel(const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------
+// Reference-order gGrid (cs_problem.grad_order == 1): one thread per (cell, point), channels
+// in order, corners in order (x bit fastest), the products and fused multiply-adds written
+// exactly as the reference / ATen write them:
+//     gix -= nw_val * (iy_se - iy) * gOut      ->   t = nw_val * wy ;  gix = fma(-t, gOut, gix)
+// (cu2d:476-495, cu3d:525-572; nvcc contracts a - b*c into an fma in both code bases), and
+// gGrid = mult * gix [* k'] at the end (cu2d:502-503).  Not a fast path: it exists so that the
+// linear / multicell=False backward can be compared bit for bit with torch grid_sample.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) cs_backward_reforder_kernel(const cs::StageParams p) {
+    constexpr int NCORN = 1 << DIM;
+    const long long total = (long long)p.N * p.P;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx / p.P);
+        const long long pi = idx - (long long)n * p.P;
+        const float off = __ldg(p.offset + n);
+        const float* gp = p.grid + (long long)n * p.grid_sn + pi * DIM;
+        cs::AxisRec ar[DIM];
+        bool ok = true;
+        int base = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            ar[a] = cs::axis_setup(__ldg(gp + a), p.size[a], off, p, p.align != 0, 1);
+            ok = ok && ar[a].ok;
+            base += ar[a].l * p.tstride[a];
+        }
+        float gg[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) gg[a] = 0.f;
+        const float* Vn = p.V + (long long)n * p.cell_stride;
+        for (int c = 0; c < p.C; ++c) {
+            const float g = __ldg(p.x1 + n * p.x1_sn + (long long)c * p.x1_sc + pi);
+#pragma unroll
+            for (int q = 0; q < NCORN; ++q) {
+                int b[DIM];
+                bool valid = ok;
+                int texel = base;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    b[a] = (q >> a) & 1;
+                    const int la = ar[a].l + b[a];
+                    valid = valid && (la >= 0) && (la < p.size[a]);
+                    texel += b[a] * p.tstride[a];
+                }
+                if (!valid) continue;
+                const float v = __ldg(Vn + (long long)texel * p.texel_stride + (long long)c * p.chan_stride);
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    float t = v;
+#pragma unroll
+                    for (int o = 0; o < DIM; ++o)
+                        if (o != a) t = __fmul_rn(t, b[o] ? ar[o].w1 : ar[o].w0);
+                    gg[a] = __fmaf_rn(b[a] ? t : -t, g, gg[a]);
+                }
+            }
+        }
+        float* out = p.ggrid + ((long long)n * p.P + pi) * DIM;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) out[a] = __fmul_rn(ar[a].d, gg[a]);   // d = mult * k'  (k' = 1 when linear)
+    }
+}
+
+int launch_reforder(const cs_problem* pb, const cs::StageParams& p, void* stream) {
+    const long long total = (long long)p.N * p.P;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) return 0;
+    if (pb->dim == 2) cs_backward_reforder_kernel<2><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else cs_backward_reforder_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "reference-order backward launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 int layout_launch(const float* src, float* dst, int N, int C, long long T, int mode, void* stream) {
     if (N < 0 || C < 0 || T < 0) return fail(CS_EINVAL, "negative size");
     if (N == 0 || C == 0 || T == 0) return 0;
@@ -207,6 +285,12 @@ int cs_backward(const cs_problem* pb, cs_stream gOut, const float* input, const 
     if (!gInput && !gGrid) return 0;
     p.V = input; p.acc = gInput; p.ggrid = gGrid;
     p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (pb->grad_order == 1 && gGrid) {
+        // gGrid in reference order by the per-pair kernel, gInput (if wanted) by the regular one
+        if (int rc = launch_reforder(pb, p, stream)) return rc;
+        if (!gInput) return 0;
+        p.ggrid = nullptr;
+    }
     return run(pb, p, cs::ST_B, false, false, stream);
 }
 

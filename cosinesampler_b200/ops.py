@@ -74,6 +74,17 @@ def set_small_cell(mode):
     _SMALL_CELL = {"auto": 0, "never": 1, "always": 2}[mode]
 
 
+_GRAD_ORDER = 0
+
+
+def set_grad_order(mode):
+    """'fast' (default) or 'reference': compute gGrid of the first backward channel by channel in
+    the reference's / ATen's operation order (one thread per pair; slower, bit-comparable with
+    torch.nn.functional.grid_sample for the linear kernel without multicell)."""
+    global _GRAD_ORDER
+    _GRAD_ORDER = {"fast": 0, "reference": 1}[mode]
+
+
 def set_lanes(lanes):
     """0 = automatic; 1/2/4/8 lanes per point quad (1 = whole channel loop in one thread)."""
     global _LANES
@@ -248,6 +259,7 @@ def _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multice
     pb.grid_stride_n = grid_sn
     pb.lanes = _LANES
     pb.small_cell = _SMALL_CELL
+    pb.grad_order = _GRAD_ORDER
     return pb
 
 

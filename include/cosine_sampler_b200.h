@@ -77,6 +77,11 @@ typedef struct cs_problem {
     int32_t lanes;         /* 0 = auto; else 1,2,4,8 lanes cooperating on one point quad */
     int32_t small_cell;    /* 0 = auto: cells whose fields fit in shared memory take the shared-memory
                               kernel; 1 = never; 2 = whenever it fits */
+    int32_t grad_order;    /* cs_backward only.  0 = fast (channels split over lanes, shuffle reduction);
+                              1 = reference order: gGrid accumulated channel by channel, corner by corner
+                              with the reference's operation order (cu2d:464-503, ATen GridSampler.cu),
+                              one thread per (cell, point) -- bit-comparable with torch grid_sample */
+    int32_t reserved;
 } cs_problem;
 
 /* Strided view of a [N, C, P] point stream whose P axis is contiguous.

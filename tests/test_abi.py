@@ -47,7 +47,7 @@ def test_struct_layout_matches_c(tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(cs_problem), offsetof(cs_problem, P),
          offsetof(cs_problem, padding_mode), offsetof(cs_problem, field_layout),
-         offsetof(cs_problem, grid_stride_n), offsetof(cs_problem, small_cell), sizeof(cs_stream));
+         offsetof(cs_problem, grid_stride_n), offsetof(cs_problem, grad_order), sizeof(cs_stream));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -55,7 +55,7 @@ int main(void) {
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     P = _lib.Problem
     want = [ctypes.sizeof(P), P.P.offset, P.padding_mode.offset, P.field_layout.offset,
-            P.grid_stride_n.offset, P.small_cell.offset, ctypes.sizeof(_lib.Stream3)]
+            P.grid_stride_n.offset, P.grad_order.offset, ctypes.sizeof(_lib.Stream3)]
     assert got == want
 
 

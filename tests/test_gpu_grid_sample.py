@@ -43,7 +43,17 @@ def test_linear_no_multicell_equals_grid_sample(cuda, dim, shape, P):
     assert_close_scaled(gG, rG, "gGrid vs grid_sample")
     assert_close_scaled(gI, rI, "gInput vs grid_sample")
     frac = float((gG == rG).float().mean())
-    print("gGrid bit-equal fraction: %.4f" % frac)
+    print("gGrid bit-equal fraction (fast order): %.4f" % frac)
+    # reference order: channels in sequence, ATen's products and fmas -> bit-identical gGrid
+    from cosinesampler_b200 import ops
+    ops.set_grad_order("reference")
+    try:
+        gG2 = torch.autograd.grad(S.apply(inp, grid, "zeros", True, name, False), grid, gOut)[0]
+    finally:
+        ops.set_grad_order("fast")
+    frac2 = float((gG2 == rG).float().mean())
+    print("gGrid bit-equal fraction (reference order): %.6f" % frac2)
+    assert torch.equal(gG2, rG), "reference-order gGrid must be bit-identical to ATen (%.6f equal)" % frac2
 
 
 def test_zero_padding_out_of_range_equals_grid_sample(cuda):
