@@ -30,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
+
 WORKLOADS = {
     # name: (dim, cells shape, total points, chunk, kernel name, residual)
     "cfg5": (2, (4, 16, 256, 256), 2 ** 25, 2 ** 20, "cosine", "helmholtz"),
@@ -285,7 +287,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample, repeats=2)
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,10 +369,22 @@ def run_reference(args):
         "cpu_baseline": desc,
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout for the one JSON line: libraries (NCCL prints its version banner there) get
+    stderr instead.  Returns a file object bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
 
 
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
