@@ -82,10 +82,6 @@ int setup(const cs_problem* pb, cs::StageParams& p, const float* grid, const flo
     return 0;
 }
 
-bool stream_vec_ok(const cs_stream& s) {
-    return s.ptr == nullptr || (aligned16(s.ptr) && s.stride_n % 4 == 0 && s.stride_c % 4 == 0);
-}
-
 int run(const cs_problem* pb, cs::StageParams& p, int stage, bool has_u, bool has_x2, void* stream) {
     if (p.N == 0 || p.C == 0 || p.P == 0) return 0;   // empty problem: nothing to launch (cu2d:904)
     // field vector width

@@ -393,13 +393,13 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
 //   work item  = (tile, channel-vector iteration jj); a tile is PTS points of one cell
 //   stage      = PG of the 4 points a lane owns in the item (NST = 4/PG stages per item)
 //
-// Everything a stage needs from global memory -- the 2^dim corner vectors of PG points
-// (and of gOutInput), plus once per item the lane's slice of the gOut / gOutggOut
-// streams -- is fetched with cp.async (LDGSTS, 16 B per lane, zero-fill for corners that
+// The random part of a stage's input -- the 2^dim corner vectors of PG points (and of
+// gOutInput) -- is fetched with cp.async (LDGSTS, 16 B per lane, zero-fill for corners that
 // are out of bounds) into lane-private shared-memory slots, one stage ahead of its use.
-// The data in flight lives in shared memory, not in registers, so a warp keeps
-// PG*2^dim*16 B per lane in flight while it computes the previous stage, and phase 1 of
-// the next tile (index map, sincospif, coefficients) also overlaps the gathers.
+// The gathers in flight live in shared memory, not in registers, so a warp keeps
+// PG*2^dim*16 B per lane in flight while it computes the previous stage; phase 1 of the next
+// tile (index map, sincospif, coefficients) and the plain coalesced prefetch of the next
+// item's slice of the gOut / gOutggOut streams (registers) overlap with them.
 // ---------------------------------------------------------------------------
 #ifndef CS_THREADS
 #define CS_THREADS 128
@@ -417,16 +417,6 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
 #define CS_PG3 1
 #endif
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 16 : 0;                       // src-size 0 -> 16 bytes of zeros
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
@@ -440,11 +430,9 @@ template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2> stru
     static constexpr int PG = (DIM == 2) ? CS_PG2 : CS_PG3;  // points per stage
     static constexpr int NST = 4 / PG;
     static constexpr int GSLOTS = PG * NCORN * (HAS_U ? 2 : 1);   // gather slots per stage (V then U)
-    static constexpr int XSLOTS = 0;                         // streams are prefetched into registers
     static constexpr int REC = 2 * RL::FIELDS4 * PTS;        // records, double-buffered by tile
     static constexpr int GBUF = 2 * GSLOTS * 32;             // gathers, double-buffered by stage
-    static constexpr int XBUF = 2 * XSLOTS * 32;             // streams, double-buffered by item
-    static constexpr int TOTAL = REC + GBUF + XBUF;          // float4 per warp
+    static constexpr int TOTAL = REC + GBUF;                 // float4 per warp
 };
 
 // cp.async with a precomputed 32-bit shared address

@@ -158,9 +158,6 @@ def _as_stream(t, P, name):
     return t, _lib.Stream3(t.data_ptr(), t.stride(0), t.stride(1))
 
 
-_NULL_STREAM = None
-
-
 def _null_stream():
     return _lib.Stream3(None, 0, 0)
 

@@ -1,5 +1,7 @@
 #!/bin/bash
-# final-ish evidence pass: tests, smoke, bench (ours + reference arm), launch list, full ncu capture
+# The GPU evidence pass of a round (run under gpurun): parity tests, smoke, stage timings vs the
+# reference CUDA op, bench (device-resident + e2e), ncu launch list and full captures.  ncu reports
+# are exported to CSV on the box and deleted (gpurun_out/ may not exceed 64 MiB).
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --maxfail 25 --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"
