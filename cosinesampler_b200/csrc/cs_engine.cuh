@@ -408,7 +408,7 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
 #define CS_MIN_BLOCKS 3
 #endif
 #ifndef CS_MIN_BLOCKS_3D
-#define CS_MIN_BLOCKS_3D 2
+#define CS_MIN_BLOCKS_3D 3
 #endif
 #ifndef CS_PG2
 #define CS_PG2 2
@@ -488,6 +488,8 @@ __device__ __forceinline__ void issue_stage(const float4* rec, int q, int st, co
 // Consume stage `st`: contract the gathered corner vectors of PG points.
 // SMEMF: the fields (V, U, accumulator) of the cell live in shared memory (small-cell kernel):
 // corner vectors are read straight from there and the scatter uses shared-memory atomics.
+// Corners are handled four at a time (one float4 of each coefficient), which keeps the live
+// state of a 3D point (8 corners) at the size of a 2D one.
 template <int DIM, int VEC, int STAGE, int PG, int PTS, bool HAS_U, bool HAS_X2, bool ALLV, bool SMEMF = false>
 __device__ __forceinline__ void consume_stage(const float4* rec, const float4* gb, int q, int lane, int st,
                                               const ItemCtx& ic, const int (&coff)[1 << DIM],
@@ -508,122 +510,115 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
             if (!ALLV) mask = __float_as_int(hd.y);
         }
         if (!ALLV && mask == 0) continue;
-        float4 k0[CQ];
 #pragma unroll
-        for (int h = 0; h < CQ; ++h) k0[h] = rec[(1 + h) * PTS + ri];
-        float vv[NCORN][VEC], uu[HAS_U ? NCORN : 1][VEC];
+        for (int h = 0; h < CQ; ++h) {
+            const float4 k0 = rec[(1 + h) * PTS + ri];          // coefficient 0 of corners 4h..4h+3
+            float vv[4][VEC], uu[HAS_U ? 4 : 1][VEC];
 #pragma unroll
-        for (int c = 0; c < NCORN; ++c) {
-            if (SMEMF) {
-                const bool valid = ALLV || ((mask >> c) & 1);
-                const long long fo = (long long)(valid ? base + coff[c] : 0) * ic.tsb;
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = 4 * h + cc;
+                if (SMEMF) {
+                    const bool valid = ALLV || ((mask >> c) & 1);
+                    const long long fo = (long long)(valid ? base + coff[c] : 0) * ic.tsb;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) { vv[c][k] = 0.f; if (HAS_U) uu[HAS_U ? c : 0][k] = 0.f; }
-                if (valid) {
-                    if (VEC == 4) {
-                        if (need_v) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(ic.vsrc + fo);
-                            vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
+                    for (int k = 0; k < VEC; ++k) { vv[cc][k] = 0.f; if (HAS_U) uu[HAS_U ? cc : 0][k] = 0.f; }
+                    if (valid) {
+                        if (VEC == 4) {
+                            if (need_v) {
+                                const float4 a4 = *reinterpret_cast<const float4*>(ic.vsrc + fo);
+                                vv[cc][0] = a4.x; vv[cc][1 % VEC] = a4.y; vv[cc][2 % VEC] = a4.z; vv[cc][3 % VEC] = a4.w;
+                            }
+                            if (HAS_U) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(ic.usrc + fo);
+                                uu[HAS_U ? cc : 0][0] = b4.x; uu[HAS_U ? cc : 0][1 % VEC] = b4.y;
+                                uu[HAS_U ? cc : 0][2 % VEC] = b4.z; uu[HAS_U ? cc : 0][3 % VEC] = b4.w;
+                            }
+                        } else {
+                            if (need_v) vv[cc][0] = *reinterpret_cast<const float*>(ic.vsrc + fo);
+                            if (HAS_U) uu[HAS_U ? cc : 0][0] = *reinterpret_cast<const float*>(ic.usrc + fo);
                         }
-                        if (HAS_U) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(ic.usrc + fo);
-                            uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
-                            uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
-                        }
-                    } else {
-                        if (need_v) vv[c][0] = *reinterpret_cast<const float*>(ic.vsrc + fo);
-                        if (HAS_U) uu[HAS_U ? c : 0][0] = *reinterpret_cast<const float*>(ic.usrc + fo);
                     }
+                } else if (VEC == 4) {
+                    if (need_v) {
+                        const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
+                        vv[cc][0] = a4.x; vv[cc][1 % VEC] = a4.y; vv[cc][2 % VEC] = a4.z; vv[cc][3 % VEC] = a4.w;
+                    }
+                    if (HAS_U) {
+                        const float4 b4 = gb[((PG + s) * NCORN + c) * 32 + lane];
+                        uu[HAS_U ? cc : 0][0] = b4.x; uu[HAS_U ? cc : 0][1 % VEC] = b4.y;
+                        uu[HAS_U ? cc : 0][2 % VEC] = b4.z; uu[HAS_U ? cc : 0][3 % VEC] = b4.w;
+                    }
+                } else {
+                    if (need_v) vv[cc][0] = gb[(s * NCORN + c) * 32 + lane].x;
+                    if (HAS_U) uu[HAS_U ? cc : 0][0] = gb[((PG + s) * NCORN + c) * 32 + lane].x;
                 }
-            } else if (VEC == 4) {
-                if (need_v) {
-                    const float4 a4 = gb[(s * NCORN + c) * 32 + lane];
-                    vv[c][0] = a4.x; vv[c][1 % VEC] = a4.y; vv[c][2 % VEC] = a4.z; vv[c][3 % VEC] = a4.w;
+            }
+            if (want_y) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float cy = f4get(k0, cc);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y[t][k] = fmaf(vv[cc][k], cy, y[t][k]);
                 }
                 if (HAS_U) {
-                    const float4 b4 = gb[((PG + s) * NCORN + c) * 32 + lane];
-                    uu[HAS_U ? c : 0][0] = b4.x; uu[HAS_U ? c : 0][1 % VEC] = b4.y;
-                    uu[HAS_U ? c : 0][2 % VEC] = b4.z; uu[HAS_U ? c : 0][3 % VEC] = b4.w;
-                }
-            } else {
-                if (need_v) vv[c][0] = gb[(s * NCORN + c) * 32 + lane].x;
-                if (HAS_U) uu[HAS_U ? c : 0][0] = gb[((PG + s) * NCORN + c) * 32 + lane].x;
-            }
-        }
-        if (want_y) {
-#pragma unroll
-            for (int c = 0; c < NCORN; ++c) {
-                const float cy = f4get(k0[c >> 2], c & 3);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) y[t][k] = fmaf(vv[c][k], cy, y[t][k]);
-            }
-            if (HAS_U) {
-#pragma unroll
-                for (int h = 0; h < CQ; ++h) {
                     const float4 ku = rec[(1 + (1 + DIM) * CQ + h) * PTS + ri];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
                         for (int k = 0; k < VEC; ++k)
-                            y[t][k] = fmaf(uu[HAS_U ? 4 * h + cc : 0][k], f4get(ku, cc), y[t][k]);
+                            y[t][k] = fmaf(uu[HAS_U ? cc : 0][k], f4get(ku, cc), y[t][k]);
                 }
             }
-        }
-        if (want_g) {
-            float dot[NCORN];
+            if (want_g) {
+                float dot[4];
 #pragma unroll
-            for (int c = 0; c < NCORN; ++c) {
-                dot[c] = 0.f;
+                for (int cc = 0; cc < 4; ++cc) {
+                    dot[cc] = 0.f;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) dot[c] = fmaf(vv[c][k], x1[t][k], dot[c]);
-            }
+                    for (int k = 0; k < VEC; ++k) dot[cc] = fmaf(vv[cc][k], x1[t][k], dot[cc]);
+                }
 #pragma unroll
-            for (int a = 0; a < DIM; ++a)
-#pragma unroll
-                for (int h = 0; h < CQ; ++h) {
+                for (int a = 0; a < DIM; ++a) {
                     const float4 kg = rec[(1 + (1 + a) * CQ + h) * PTS + ri];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                    for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[cc], f4get(kg, cc), gg[t][a]);
                 }
-            if (HAS_U && DIM == 3) {
+                if (HAS_U && DIM == 3) {
 #pragma unroll
-                for (int c = 0; c < NCORN; ++c) {
-                    dot[c] = 0.f;
+                    for (int cc = 0; cc < 4; ++cc) {
+                        dot[cc] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) dot[c] = fmaf(uu[HAS_U ? c : 0][k], x1[t][k], dot[c]);
-                }
+                        for (int k = 0; k < VEC; ++k) dot[cc] = fmaf(uu[HAS_U ? cc : 0][k], x1[t][k], dot[cc]);
+                    }
 #pragma unroll
-                for (int a = 0; a < DIM; ++a)
-#pragma unroll
-                    for (int h = 0; h < CQ; ++h) {
+                    for (int a = 0; a < DIM; ++a) {
                         const float4 kg = rec[(1 + (2 + DIM + a) * CQ + h) * PTS + ri];
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[4 * h + cc], f4get(kg, cc), gg[t][a]);
+                        for (int cc = 0; cc < 4; ++cc) gg[t][a] = fmaf(dot[cc], f4get(kg, cc), gg[t][a]);
                     }
+                }
             }
-        }
-        if (want_s) {
-            float4 k1[CQ];
-            if (HAS_X2) {
+            if (want_s) {
+                float4 k1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_X2) k1 = rec[(1 + CQ + h) * PTS + ri];
 #pragma unroll
-                for (int h = 0; h < CQ; ++h) k1[h] = rec[(1 + CQ + h) * PTS + ri];
-            }
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = 4 * h + cc;
+                    if (ALLV || ((mask >> c) & 1)) {
+                        const float cs1 = f4get(k0, cc);
+                        float sv[VEC];
 #pragma unroll
-            for (int c = 0; c < NCORN; ++c) {
-                if (ALLV || ((mask >> c) & 1)) {
-                    const float cs1 = f4get(k0[c >> 2], c & 3);
-                    float sv[VEC];
+                        for (int k = 0; k < VEC; ++k) {
+                            sv[k] = x1[t][k] * cs1;
+                            if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1, cc), sv[k]);
+                        }
+                        float* dst = reinterpret_cast<float*>(ic.adst + (long long)(base + coff[c]) * ic.tsb);
+                        if (SMEMF) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        sv[k] = x1[t][k] * cs1;
-                        if (HAS_X2) sv[k] = fmaf(x2[t][k], f4get(k1[c >> 2], c & 3), sv[k]);
-                    }
-                    float* dst = reinterpret_cast<float*>(ic.adst + (long long)(base + coff[c]) * ic.tsb);
-                    if (SMEMF) {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) atomicAdd(dst + k, sv[k]);    // red.shared.add.f32
-                    } else {
-                        FieldVec<VEC>::red(dst, sv);
+                            for (int k = 0; k < VEC; ++k) atomicAdd(dst + k, sv[k]);    // red.shared.add.f32
+                        } else {
+                            FieldVec<VEC>::red(dst, sv);
+                        }
                     }
                 }
             }
