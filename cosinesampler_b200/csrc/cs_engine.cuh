@@ -407,6 +407,9 @@ __device__ __forceinline__ void build_record(float4* rec4, int i, const PointIn<
 #ifndef CS_MIN_BLOCKS
 #define CS_MIN_BLOCKS 3
 #endif
+#ifndef CS_MIN_BLOCKS_GATHER
+#define CS_MIN_BLOCKS_GATHER 4
+#endif
 #ifndef CS_MIN_BLOCKS_3D
 #define CS_MIN_BLOCKS_3D 3
 #endif
@@ -626,8 +629,12 @@ __device__ __forceinline__ void consume_stage(const float4* rec, const float4* g
     }
 }
 
-template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
-__global__ void __launch_bounds__(CS_THREADS, (DIM == 2 ? CS_MIN_BLOCKS : CS_MIN_BLOCKS_3D))
+// SCAT: this instantiation can scatter into the accumulator.  Gather-only calls (u_x, u_xx: the
+// majority of a PDE step) run the SCAT = false instantiation, which carries no reduction code,
+// needs fewer registers and is compiled for one more resident block per SM.
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2, bool SCAT>
+__global__ void __launch_bounds__(CS_THREADS, (DIM == 2 ? (SCAT ? CS_MIN_BLOCKS : CS_MIN_BLOCKS_GATHER)
+                                                        : CS_MIN_BLOCKS_3D))
 cs_stage_kernel(const StageParams p) {
     using RL = RecLayout<DIM, STAGE, HAS_U, HAS_X2>;
     using WS = WarpSmem<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
@@ -654,7 +661,7 @@ cs_stage_kernel(const StageParams p) {
 
     const bool want_y = (p.y != nullptr);
     const bool want_g = (p.ggrid != nullptr) && (STAGE == ST_B || STAGE == ST_BB);
-    const bool want_s = (p.acc != nullptr) && HAS_X1;
+    const bool want_s = SCAT && (p.acc != nullptr) && HAS_X1;
     const bool need_v = want_y || want_g;
     const bool svec = p.svec4 != 0;
     const int V = p.C / VEC;                       // channel vectors per texel; L divides V (API)

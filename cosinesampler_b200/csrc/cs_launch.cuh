@@ -68,14 +68,10 @@ bool try_launch_small(const StageParams& p, cudaStream_t stream, cudaError_t& er
     return true;
 }
 
-template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
-cudaError_t launch_one(const StageParams& p, cudaStream_t stream) {
-    {
-        cudaError_t err = cudaSuccess;
-        if (try_launch_small<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>(p, stream, err)) return err;
-    }
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2, bool SCAT>
+cudaError_t launch_global(const StageParams& p, cudaStream_t stream) {
     using WS = WarpSmem<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
-    auto kern = cs_stage_kernel<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>;
+    auto kern = cs_stage_kernel<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2, SCAT>;
     constexpr size_t smem_per_warp = (size_t)WS::TOTAL * sizeof(float4);
     // block size: as many warps as fit CS_SMEM_TARGET bytes of shared memory, at most
     // CS_THREADS threads; several blocks then share an SM
@@ -102,6 +98,19 @@ cudaError_t launch_one(const StageParams& p, cudaStream_t stream) {
     if (blocks < 1) return cudaSuccess;
     kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int DIM, int VEC, int LSHIFT, int STAGE, bool HAS_U, bool HAS_X2>
+cudaError_t launch_one(const StageParams& p, cudaStream_t stream) {
+    {
+        cudaError_t err = cudaSuccess;
+        if (try_launch_small<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2>(p, stream, err)) return err;
+    }
+    constexpr bool can_scatter = (STAGE != ST_F);
+    if (can_scatter && p.acc != nullptr)
+        return launch_global<DIM, VEC, LSHIFT, STAGE, HAS_U, HAS_X2, can_scatter>(p, stream);
+    // the fused b_input stream only feeds the scatter: a gather-only BBB never has it
+    return launch_global<DIM, VEC, LSHIFT, STAGE, HAS_U, false, false>(p, stream);
 }
 
 template <int DIM, int VEC, int LSHIFT>
