@@ -45,12 +45,16 @@ CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tenso
 
 def ncu_traffic_bytes(label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a stage kernel, from the committed
-    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg3_summary.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1", "ncu_stages_cfg3_summary.json")) as f:
-            return int(json.load(f)["kernels"][label]["traffic_bytes"])
-    except Exception:
-        return None
+    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg{3,4}_summary.json)."""
+    for name in ("ncu_stages_cfg3_summary.json", "ncu_stages_cfg4_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1", name)) as f:
+                kernels = json.load(f)["kernels"]
+            if label in kernels:
+                return int(kernels[label]["traffic_bytes"])
+        except Exception:
+            pass
+    return None
 
 
 def measured_peak_gbs():
