@@ -32,9 +32,15 @@
 //     128-bit broadcasts (one float4 = the 4 corners of a coefficient).  Neither
 //     the transcendental work nor the coefficient products are replicated over
 //     the L lanes of a quad, and phase 2 is nothing but address + gather + fma.
+//   * the random corner gathers run through a per-warp cp.async ring (one stage
+//     ahead, data in flight in shared memory), the streams are prefetched one
+//     item ahead with plain loads; warps never synchronise with each other.
 //   * persistent grid: blocks loop over tiles, cell index fastest so that the N
 //     cells of one point (which share coordinates and an expanded gOut in
-//     PIXEL) are in flight together.
+//     PIXEL) are in flight together -- or cell by cell when the fields touched
+//     at random would not fit in L2 together (StageParams::cell_major).
+//   * cs_small_kernel (end of this file) is the variant for cells that fit in
+//     shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
