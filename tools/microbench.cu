@@ -111,6 +111,18 @@ int main() {
             float ms = time_ms([&] { red_kernel<4, true><<<sm * 8, 256>>>((float*)A, nseg, groups); }, 10);
             printf("{\"bench\": \"red_v4_64B_L4\", \"table_MiB\": %zu, \"ms\": %.4f, \"Gseg_per_s\": %.2f, \"GBps\": %.1f}\n",
                    table_mib, ms, groups / ms / 1e6, groups * 64.0 / ms / 1e6);
+            {
+                uint32_t nseg8 = bytes / 128;
+                long long g8 = groups / 2;
+                float ms8 = time_ms([&] { red_kernel<8, true><<<sm * 8, 256>>>((float*)A, nseg8, g8); }, 10);
+                printf("{\"bench\": \"red_v4_128B_L8\", \"table_MiB\": %zu, \"ms\": %.4f, \"Gseg_per_s\": %.2f, \"GBps\": %.1f}\n",
+                       table_mib, ms8, g8 / ms8 / 1e6, g8 * 128.0 / ms8 / 1e6);
+                uint32_t nseg2 = bytes / 32;
+                long long g2 = groups * 2;
+                float ms2 = time_ms([&] { red_kernel<2, true><<<sm * 8, 256>>>((float*)A, nseg2, g2); }, 10);
+                printf("{\"bench\": \"red_v4_32B_L2\", \"table_MiB\": %zu, \"ms\": %.4f, \"Gseg_per_s\": %.2f, \"GBps\": %.1f}\n",
+                       table_mib, ms2, g2 / ms2 / 1e6, g2 * 32.0 / ms2 / 1e6);
+            }
             ms = time_ms([&] { red_kernel<4, false><<<sm * 8, 256>>>((float*)A, nseg, groups); }, 5);
             printf("{\"bench\": \"red_scalar_64B_L4\", \"table_MiB\": %zu, \"ms\": %.4f, \"Gseg_per_s\": %.2f, \"GBps\": %.1f}\n",
                    table_mib, ms, groups / ms / 1e6, groups * 64.0 / ms / 1e6);
