@@ -190,13 +190,38 @@ def run_ours(args):
 
     loss_host = torch.zeros(1, pin_memory=True)
 
+    copy_stream = torch.cuda.Stream(device=device)
+
     def step_e2e():
+        """Same step from HOST buffers: every chunk of coordinates is copied from pinned host
+        memory inside the timed region (on a copy stream, one chunk ahead of the compute stream) and
+        the step's loss is read back to the host."""
         stepper.zero_grad()
-        dev = coords_pinned.to(device, non_blocking=True)              # H2D inside the timed region
-        cols = [dev[:, a:a + 1] for a in range(dim)]
-        loss = stepper.step(cols, total)
-        loss_host.copy_(loss.reshape(1), non_blocking=True)            # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
+        nloc = coords_pinned.shape[0]
+        spans = [(s0, min(nloc, s0 + chunk)) for s0 in range(0, nloc, chunk)]
+        cur = torch.cuda.current_stream()
+
+        def fetch(span):
+            with torch.cuda.stream(copy_stream):
+                t = coords_pinned[span[0]:span[1]].to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
+
+        nxt = fetch(spans[0])
+        acc = None
+        for i, span in enumerate(spans):
+            t, ev = nxt
+            if i + 1 < len(spans):
+                nxt = fetch(spans[i + 1])
+            cur.wait_event(ev)
+            t.record_stream(cur)
+            loss = chain.training_step(sampler, cells, [t[:, a:a + 1] for a in range(dim)], head,
+                                       residual=residual, loss_scale=(span[1] - span[0]) / float(total))
+            acc = loss if acc is None else acc + loss
+        dp.allreduce_grads(stepper.params())
+        loss_host.copy_(acc.reshape(1), non_blocking=True)               # D2H of the step's result
+        cur.synchronize()
         return loss_host
 
     def barrier():
