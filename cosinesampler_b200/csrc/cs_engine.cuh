@@ -139,7 +139,11 @@ __device__ __forceinline__ AxisRec axis_setup(float g, int size, float off, cons
             i = __fmaf_rn(__fmaf_rn(__fadd_rn(g, 1.f), sf, -1.f), 0.5f, off);
         }
     }
-    a.ok = fabsf(i) < 1.0e9f;                                     // rejects NaN / inf / absurd
+    // NaN / inf are rejected (the reference's floor -> int cast is undefined there, cu2d:310-311).
+    // Huge finite indices are out of range for zeros padding (contribute nothing, like the
+    // reference), clip to the border for border padding, and are rejected for reflection (whose
+    // flip count overflows in the reference as well).
+    a.ok = (p.pad == 1) ? (fabsf(i) <= 3.0e38f) : (fabsf(i) < 1.0e9f);
     if (!a.ok) i = 0.f;
     if (p.pad == 1) {                                             // border, cu2d:220-223
         m *= clip_grad(i, size);

@@ -191,6 +191,12 @@ def test_empty_and_degenerate_inputs(cuda):
     out = ops.forward(inp, grid, off, 0, True, 0, True)
     torch.cuda.synchronize()
     assert torch.isfinite(out[..., 3]).all() and float(out[..., :3].abs().sum()) == 0.0
+    # huge finite coordinates: border padding clips them to the edge texel (cu2d:90-93), zeros drops them
+    far = torch.tensor([[[[1e20, -1e20], [3.0, -3.0], [-1e20, 0.5], [0.25, 1e20]]]], device=cuda).repeat(2, 1, 1, 1)
+    for pad in (0, 1):
+        o = ops.forward(inp, far, off, pad, True, 0, True)
+        ref = so.forward(inp.cpu(), far.cpu(), off.cpu(), pad=pad, kernel=0, multicell=True)
+        assert_close_scaled(o, ref, "huge coordinates, padding %d" % pad)
     # a 2x2 cell with multicell: index range collapses to a single interval
     tiny = torch.rand(2, 4, 2, 2, device=cuda)
     g = torch.rand(2, 1, 16, 2, device=cuda) * 2 - 1
