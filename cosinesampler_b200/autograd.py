@@ -95,6 +95,15 @@ def _push_want(want):
     _tls.want = want
 
 
+def _apply_with_want(fn, want, *args):
+    """fn.apply(*args) with the per-thread output hint set for exactly that call."""
+    _push_want(want)
+    try:
+        return fn.apply(*args)
+    finally:
+        _tls.want = None
+
+
 def _pop_want(default):
     w = getattr(_tls, "want", None)
     _tls.want = None
@@ -189,8 +198,8 @@ def make_functions(dim):
                         ctx.align_corners, gOutgInput is not None, kn, ctx.multicell,
                         staged=staged, want=(want_input, want_ggout))
                 if gOutggOut is not None and want_input:
-                    _push_want((True, False, False))
-                    b_input, _, _ = CosineSamplerBackwardBackward.apply(
+                    b_input, _, _ = _apply_with_want(
+                        CosineSamplerBackwardBackward, (True, False, False),
                         input, grid, gOutggOut, None, gOutGrid, ctx.offset, ctx.padding_mode,
                         ctx.align_corners, ctx.kernel, ctx.multicell)
                     gInput = _add(gInput, b_input)
@@ -237,8 +246,8 @@ def make_functions(dim):
                 gOutInput = gOutInput.contiguous()
             if gOutGrid is not None:
                 gOutGrid = gOutGrid.contiguous()
-            _push_want(want)
-            gInput, gGrid, ggOut = CosineSamplerBackwardBackward.apply(
+            gInput, gGrid, ggOut = _apply_with_want(
+                CosineSamplerBackwardBackward, want,
                 input, grid, gOut, gOutInput, gOutGrid, ctx.offset, ctx.padding_mode,
                 ctx.align_corners, ctx.kernel, ctx.multicell)
             return gInput, gGrid, ggOut, None, None, None, None, None
@@ -273,8 +282,8 @@ def make_functions(dim):
             want = (_engine_wants(ctx, 0), _engine_wants(ctx, 1))
             if not any(want):
                 return None, None, None, None, None, None
-            _push_want(want)
-            d_input, d_grid = CosineSamplerBackward.apply(
+            d_input, d_grid = _apply_with_want(
+                CosineSamplerBackward, want,
                 input, grid, gradOut, ctx.offset, ctx.padding_mode, ctx.align_corners, ctx.kernel,
                 ctx.multicell)
             return d_input, d_grid, None, None, None, None
