@@ -14,6 +14,7 @@ EXPORTS = (
     "cs_version", "cs_last_error", "cs_launch_count",
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
+    "cs_jet_forward", "cs_jet_backward",
 )
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
@@ -72,6 +73,10 @@ def load():
     lib.cs_backward_backward.argtypes = [pp, vp, vp, vp, vp, Stream3, vp, vp, vp, vp, vp]
     lib.cs_backward_backward_backward.restype = ctypes.c_int
     lib.cs_backward_backward_backward.argtypes = [pp, vp, vp, Stream3, vp, vp, Stream3, vp, vp, vp, vp]
+    lib.cs_jet_forward.restype = ctypes.c_int
+    lib.cs_jet_forward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
+    lib.cs_jet_backward.restype = ctypes.c_int
+    lib.cs_jet_backward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
     lib.cs_to_channel_last.restype = ctypes.c_int
     lib.cs_to_channel_last.argtypes = [vp, vp, i32, i32, i64, vp]
     lib.cs_from_channel_last.restype = ctypes.c_int

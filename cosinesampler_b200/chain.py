@@ -65,9 +65,31 @@ def pde_loss(sampler, cells, coords, head, residual="helmholtz", k2=math.pi ** 2
     return torch.mean(f ** 2)
 
 
+def _residual(u, first, second, residual, k2):
+    if residual == "t2d":
+        return first[1] * 2 + 5 * (u ** 3) - 5 * u - 0.0001 * second[0]
+    f = (k2 if residual == "helmholtz" else 1.0) * u
+    for s2 in second:
+        f = f + s2
+    return f
+
+
+def jet_pde_loss(jet_sampler, cells, coords, head, residual="helmholtz", k2=math.pi ** 2):
+    """The same loss as `pde_loss`, through the fused jet operator (`jet.SamplerJet2d/3d`):
+    one gather pass yields z, z_a, z_aa summed over the cells, the head's chain rule is applied
+    to the jets (`jet.jet_mlp`), and a single first-order backward scatters into the cells.
+    `jet_sampler(cells, coords[P,dim]) -> jets [1+2*dim, C, P]`; `coords` is the list of [P,1]
+    columns `pde_loss` takes."""
+    from .jet import jet_mlp
+    dim = len(coords)
+    jets = jet_sampler(cells, torch.cat([c.detach() for c in coords], -1))
+    u, first, second = jet_mlp(head, jets, dim, order=2)
+    return torch.mean(_residual(u, first, second, residual, k2) ** 2)
+
+
 def training_step(sampler, cells, coords, head, residual="helmholtz", k2=math.pi ** 2,
-                  chunk=None, loss_scale=1.0):
-    """One fwd -> triple-bwd step: accumulates d loss / d cells (and head grads) into
+                  chunk=None, loss_scale=1.0, jet=False):
+    """One fwd -> triple-bwd step (jet=True: `sampler` is a jet sampler, see `jet_pde_loss`): accumulates d loss / d cells (and head grads) into
     `.grad`.  `coords` is a list of [P,1] tensors (no grad needed); points are processed
     in chunks of `chunk` so that the [N,C,P] streams stay bounded.  Returns the loss
     (a 0-dim tensor, mean over all points, scaled by loss_scale)."""
@@ -79,8 +101,12 @@ def training_step(sampler, cells, coords, head, residual="helmholtz", k2=math.pi
     total = None
     for s in range(0, P, chunk):
         e = min(P, s + chunk)
-        cs = [c[s:e].detach().requires_grad_(True) for c in coords]
-        loss = pde_loss(sampler, cells, cs, head, residual, k2) * (loss_scale * (e - s) / P)
+        if jet:
+            loss = jet_pde_loss(sampler, cells, [c[s:e] for c in coords], head, residual, k2)
+        else:
+            cs = [c[s:e].detach().requires_grad_(True) for c in coords]
+            loss = pde_loss(sampler, cells, cs, head, residual, k2)
+        loss = loss * (loss_scale * (e - s) / P)
         loss.backward(inputs=params)
         total = loss.detach() if total is None else total + loss.detach()
     return total

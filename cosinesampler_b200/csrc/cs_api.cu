@@ -9,6 +9,7 @@
 
 #include "../../include/cosine_sampler_b200.h"
 #include "cs_engine.cuh"
+#include "cs_jet.cuh"
 
 namespace cs {
 // one function per (dim, field vector width, log2 lanes) variant, each in its own object file
@@ -17,6 +18,10 @@ CS_DECL(launch_d2_v4_l0) CS_DECL(launch_d2_v4_l1) CS_DECL(launch_d2_v4_l2) CS_DE
 CS_DECL(launch_d3_v4_l0) CS_DECL(launch_d3_v4_l1) CS_DECL(launch_d3_v4_l2) CS_DECL(launch_d3_v4_l3)
 CS_DECL(launch_d2_v1_l0) CS_DECL(launch_d3_v1_l0)
 #undef CS_DECL
+#define CS_DECLJ(name) cudaError_t name(int order, bool backward, JetParams& p, cudaStream_t s);
+CS_DECLJ(launch_jet_d2_l0) CS_DECLJ(launch_jet_d2_l1) CS_DECLJ(launch_jet_d2_l2) CS_DECLJ(launch_jet_d2_l3)
+CS_DECLJ(launch_jet_d3_l0) CS_DECLJ(launch_jet_d3_l1) CS_DECLJ(launch_jet_d3_l2) CS_DECLJ(launch_jet_d3_l3)
+#undef CS_DECLJ
 }  // namespace cs
 
 namespace {
@@ -255,6 +260,56 @@ int layout_launch(const float* src, float* dst, int N, int C, long long T, int m
     return 0;
 }
 
+// Jet operator (cs_jet.cuh): validation shared by cs_jet_forward / cs_jet_backward.
+int jet_run(const cs_problem* pb, int order, bool backward, const float* field_in, float* field_out,
+            const float* coords, const float* offset, float* jets_out, const float* jets_in, void* stream) {
+    if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
+    if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
+    if (order != 1 && order != 2) return fail(CS_EINVAL, "jet order must be 1 or 2, got %d", order);
+    if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
+    if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
+    if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
+    if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
+    if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
+    if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
+    if (pb->N == 0 || pb->C == 0 || pb->P == 0) return 0;
+    if (pb->field_layout != CS_LAYOUT_CHANNEL_LAST)
+        return fail(CS_EUNSUPPORTED, "the jet operator needs channel-last fields (cs_to_channel_last)");
+    const int v = pb->C / 4;
+    if (pb->C % 4 != 0 || !(v == 1 || v == 2 || v == 4 || v == 8))
+        return fail(CS_EUNSUPPORTED, "the jet operator needs C in {4, 8, 16, 32}, got %d", pb->C);
+    if (!coords || !offset) return fail(CS_EINVAL, "coords/offset pointer is NULL");
+    const float* field = backward ? field_out : field_in;
+    const float* rows = backward ? jets_in : jets_out;
+    if (!field || !rows) return fail(CS_EINVAL, "field/jets pointer is NULL");
+    if (!aligned16(field)) return fail(CS_EINVAL, "field must be 16-byte aligned");
+    const long long T = (long long)pb->D * pb->H * pb->W;
+    if (T * (long long)pb->C >= (1ll << 31))
+        return fail(CS_EUNSUPPORTED, "a cell has %lld elements; the per-cell index is 32-bit", T * pb->C);
+    if (pb->P >= (1ll << 33)) return fail(CS_EUNSUPPORTED, "too many points (%lld)", (long long)pb->P);
+    cs::JetParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = pb->N; p.C = pb->C; p.P = pb->P;
+    p.size[0] = pb->W; p.size[1] = pb->H; p.size[2] = pb->D;
+    p.tstride[0] = 1; p.tstride[1] = pb->W; p.tstride[2] = pb->W * pb->H;
+    p.cell_stride = T * pb->C;
+    p.V = field_in; p.acc = field_out; p.coords = coords; p.offset = offset;
+    p.jets = jets_out; p.gjets = jets_in;
+    p.svec = (p.P % 4 == 0) && aligned16(rows);
+    p.cvec2 = (reinterpret_cast<uintptr_t>(coords) & 7u) == 0;
+    p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
+    p.multicell = pb->multicell; p.index_mode = pb->index_mode;
+    using Fn = cudaError_t (*)(int, bool, cs::JetParams&, cudaStream_t);
+    static const Fn table[2][4] = {
+        {cs::launch_jet_d2_l0, cs::launch_jet_d2_l1, cs::launch_jet_d2_l2, cs::launch_jet_d2_l3},
+        {cs::launch_jet_d3_l0, cs::launch_jet_d3_l1, cs::launch_jet_d3_l2, cs::launch_jet_d3_l3}};
+    const int lshift = (v == 1) ? 0 : (v == 2) ? 1 : (v == 4) ? 2 : 3;
+    cudaError_t e = table[pb->dim - 2][lshift](order, backward, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "jet kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -322,6 +377,16 @@ int cs_backward_backward_backward(const cs_problem* pb, const float* input, cons
     p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
     if (has_x2) { p.x2 = gOutggOut.ptr; p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
     return run(pb, p, cs::ST_BBB, false, has_x2, stream);
+}
+
+int cs_jet_forward(const cs_problem* pb, int32_t order, const float* input, const float* coords,
+                   const float* offset, float* jets, void* stream) {
+    return jet_run(pb, order, false, input, nullptr, coords, offset, jets, nullptr, stream);
+}
+
+int cs_jet_backward(const cs_problem* pb, int32_t order, const float* gJets, const float* coords,
+                    const float* offset, float* gInput, void* stream) {
+    return jet_run(pb, order, true, nullptr, gInput, coords, offset, nullptr, gJets, stream);
 }
 
 int cs_to_channel_last(const float* src, float* dst, int32_t N, int32_t C, int64_t T, void* stream) {

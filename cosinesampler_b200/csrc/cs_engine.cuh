@@ -120,7 +120,8 @@ __device__ __forceinline__ float reflect_grad(float& i, int twice_low, int twice
     return -sign;
 }
 
-__device__ __forceinline__ AxisRec axis_setup(float g, int size, float off, const StageParams& p,
+template <class ParamsT>
+__device__ __forceinline__ AxisRec axis_setup(float g, int size, float off, const ParamsT& p,
                                               bool align, int order) {
     AxisRec a;
     float i, m;

@@ -1,0 +1,539 @@
+// cs_jet.cuh -- fused multi-cell "jet" sampler (SURVEY section 8f ranks 1 + 2).
+//
+// The reference evaluates a PDE residual by calling the operator 14-20 times per step
+// (forward, a first backward per u_a, a double backward per u_aa, triple backwards to the
+// cells; modules_2d.py:38-111), each call streaming [N,C,P] tensors through HBM, and the
+// caller replicates the coordinates over the N cells and sums the result over the cells
+// (test_2d.py:38,51).  Every one of those calls evaluates, at the same corners with the
+// same per-axis kernel values, one of
+//
+//     z      = sum_n sum_q V_q w_q                    (value)
+//     z_a    = sum_n sum_q V_q D_a,q                  (d / d coordinate a)
+//     z_aa   = sum_n sum_q V_q D_aa,q                 (pure second derivative)
+//
+// (formulas: SURVEY section 7.0; cu2d:315-353, 476-503, 694-706).  The jet operator
+// produces all of them in ONE gather pass -- jets[J][C][P], J = 1 + ORDER*DIM, summed over
+// the cells inside the kernel -- and its adjoint scatters d loss / d jets back into the
+// cells in ONE scatter pass.  The caller applies the chain rule of its head to the jets
+// (cosinesampler_b200/jet.py), so a training step needs first-order autograd only.
+//
+// Work decomposition follows cs_engine.cuh: a warp owns a tile of PPQ*(32/L) consecutive
+// points, L = C/4 lanes share a quad of PPQ points, each lane holds 4 channels (one 16-byte
+// gather per corner, one red.global.add.v4.f32 per corner); the warp walks the N cells of
+// its tile and keeps the sums over the cells in registers.  Phase 1 (one point per lane)
+// writes the finished per-corner coefficients of all J jets to a shared-memory record; the
+// corner gathers run through a per-warp cp.async ring one stage ahead of their use.
+#pragma once
+#include "cs_engine.cuh"
+
+namespace cs {
+
+struct JetParams {
+    int N, C;
+    int size[3];            // extent per axis a (0:W 1:H 2:D)
+    int tstride[3];         // texel stride per axis, in texels
+    long long P;
+    long long num_ptiles;
+    long long cell_stride;  // elements between cells (T*C)
+    const float* V;         // input, channel-last [N,T,C]                   (forward)
+    float* acc;             // gInput accumulator, channel-last [N,T,C]      (backward)
+    const float* coords;    // [P,DIM]
+    const float* offset;    // [N]
+    float* jets;            // [J,C,P]                                        (forward)
+    const float* gjets;     // [J,C,P]                                        (backward)
+    int svec;               // point rows may be accessed as 16-byte vectors
+    int cvec2;              // 2D coordinates may be loaded as float2
+    int pad, align, kernel, multicell, index_mode;
+};
+
+template <int DIM, int ORDER> struct JetLayout {
+    static constexpr int NCORN = 1 << DIM;
+    static constexpr int CQ = NCORN / 4;
+    static constexpr int J = 1 + ORDER * DIM;
+    static constexpr int FIELDS4 = 1 + J * CQ;     // float4 fields per point: header + J coefficient sets
+};
+
+// Phase 1 for one (cell, point): record field 0 = (base texel, corner-valid mask);
+// field 1 + jt*CQ + h = coefficient of jet jt for corners 4h..4h+3.
+//   jt = 0: w_q     jt = 1+a: D_a,q     jt = 1+DIM+a: D_aa,q
+template <int DIM, int ORDER, int PTS>
+__device__ __forceinline__ void build_jet_record(float4* rec4, int i, const float (&g)[DIM], bool in_range,
+                                                 float off, const JetParams& p) {
+    using JL = JetLayout<DIM, ORDER>;
+    constexpr int NCORN = JL::NCORN;
+    constexpr int CQ = JL::CQ;
+    constexpr int J = JL::J;
+    int base = 0, mask = 0;
+    float coef[J][NCORN];
+#pragma unroll
+    for (int k = 0; k < J; ++k)
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) coef[k][c] = 0.f;
+    if (in_range) {
+        bool ok = true;
+        bool lo_ok[DIM], hi_ok[DIM];
+        float w[DIM][2], dw[DIM][2], ew[DIM][2];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            const AxisRec ar = axis_setup(g[a], p.size[a], off, p, p.align != 0, ORDER);
+            ok = ok && ar.ok;
+            base += ar.l * p.tstride[a];
+            lo_ok[a] = (ar.l >= 0) && (ar.l < p.size[a]);
+            hi_ok[a] = (ar.l + 1 >= 0) && (ar.l + 1 < p.size[a]);
+            w[a][0] = ar.w0; w[a][1] = ar.w1;
+            dw[a][0] = -ar.d; dw[a][1] = ar.d;
+            if (ORDER >= 2) { ew[a][0] = ar.e; ew[a][1] = -ar.e; } else { ew[a][0] = ew[a][1] = 0.f; }
+        }
+#pragma unroll
+        for (int c = 0; c < NCORN; ++c) {
+            int b[DIM];
+            bool valid = ok;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) { b[a] = (c >> a) & 1; valid = valid && (b[a] ? hi_ok[a] : lo_ok[a]); }
+            if (!valid) continue;
+            mask |= 1 << c;
+            float wo[DIM], wall;
+            if (DIM == 2) {
+                wo[0] = w[1][b[1]]; wo[1] = w[0][b[0]];
+                wall = w[0][b[0]] * w[1][b[1]];
+            } else {
+                wo[0] = w[1][b[1]] * w[2][b[2]];
+                wo[1] = w[0][b[0]] * w[2][b[2]];
+                wo[2] = w[0][b[0]] * w[1][b[1]];
+                wall = (w[0][b[0]] * w[1][b[1]]) * w[2][b[2]];
+            }
+            coef[0][c] = wall;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                coef[1 + a][c] = dw[a][b[a]] * wo[a];
+                if (ORDER >= 2) coef[1 + DIM + a][c] = ew[a][b[a]] * wo[a];
+            }
+        }
+    }
+    rec4[i] = make_float4(__int_as_float(base), __int_as_float(mask), 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < J; ++k)
+#pragma unroll
+        for (int h = 0; h < CQ; ++h)
+            rec4[(1 + k * CQ + h) * PTS + i] =
+                make_float4(coef[k][4 * h], coef[k][4 * h + 1], coef[k][4 * h + 2], coef[k][4 * h + 3]);
+}
+
+// PPQ consecutive points of one row of a [rows, P] array
+template <int PPQ>
+__device__ __forceinline__ void row_store(const float (&v)[PPQ], float* row, long long p0, long long P, bool vec) {
+    if (vec) {
+        if (p0 < P) {
+            if (PPQ == 4) __stcs(reinterpret_cast<float4*>(row + p0), make_float4(v[0], v[1 % PPQ], v[2 % PPQ], v[3 % PPQ]));
+            else __stcs(reinterpret_cast<float2*>(row + p0), make_float2(v[0], v[1 % PPQ]));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PPQ; ++i) if (p0 + i < P) __stcs(row + p0 + i, v[i]);
+    }
+}
+template <int PPQ>
+__device__ __forceinline__ void row_load(float (&v)[PPQ], const float* row, long long p0, long long P, bool vec) {
+    if (vec) {
+        if (p0 < P) {
+            if (PPQ == 4) {
+                const float4 t = __ldcs(reinterpret_cast<const float4*>(row + p0));
+                v[0] = t.x; v[1 % PPQ] = t.y; v[2 % PPQ] = t.z; v[3 % PPQ] = t.w;
+            } else {
+                const float2 t = __ldcs(reinterpret_cast<const float2*>(row + p0));
+                v[0] = t.x; v[1 % PPQ] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPQ; ++i) v[i] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PPQ; ++i) v[i] = (p0 + i < P) ? __ldcs(row + p0 + i) : 0.f;
+    }
+}
+
+template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
+    using JL = JetLayout<DIM, ORDER>;
+    static constexpr int NCORN = 1 << DIM;
+    static constexpr int PTS = PPQ * (32 >> LSHIFT);            // points per warp tile
+    static constexpr int PG = (DIM == 2 && PPQ >= 2) ? 2 : 1;    // points per pipeline stage
+    static constexpr int NST = PPQ / PG;
+    static constexpr int GSLOTS = PG * NCORN;
+    static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer (float4)
+    static constexpr int GBUF = 2 * GSLOTS * 32;                 // gather ring, double-buffered by stage
+    static constexpr int TOTAL_FWD = 2 * REC1 + GBUF;
+    static constexpr int TOTAL_BWD = REC1;
+};
+
+#ifndef CS_JET_BLOCKS_2D
+#define CS_JET_BLOCKS_2D 3
+#endif
+#ifndef CS_JET_BLOCKS_3D
+#define CS_JET_BLOCKS_3D 3
+#endif
+
+// ---------------------------------------------------------------------------
+// forward: jets[jt][c][p] = sum_n sum_q V[n][corner q][c] * coef_jt,q(n, p)
+// ---------------------------------------------------------------------------
+template <int DIM, int LSHIFT, int ORDER, int PPQ>
+__global__ void __launch_bounds__(128, (DIM == 2 ? CS_JET_BLOCKS_2D : CS_JET_BLOCKS_3D))
+cs_jet_fwd_kernel(const JetParams p) {
+    using JL = JetLayout<DIM, ORDER>;
+    using WS = JetSmem<DIM, LSHIFT, ORDER, PPQ>;
+    constexpr int NCORN = JL::NCORN;
+    constexpr int CQ = JL::CQ;
+    constexpr int J = JL::J;
+    constexpr int F4 = JL::FIELDS4;
+    constexpr int L = 1 << LSHIFT;
+    constexpr int PTS = WS::PTS;
+    constexpr int PPL = (PTS + 31) / 32;
+    constexpr int PG = WS::PG;
+    constexpr int NST = WS::NST;
+    constexpr int GS = WS::GSLOTS;
+    constexpr int FULL = (1 << NCORN) - 1;
+
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int q = lane >> LSHIFT;
+    const int j = lane & (L - 1);
+    float4* recbuf = smem4 + (size_t)warp * WS::TOTAL_FWD;   // [2][F4][PTS]
+    float4* gbuf = recbuf + 2 * WS::REC1;                    // [2][GS][32]
+    const unsigned gdst = (unsigned)__cvta_generic_to_shared(gbuf + lane);
+
+    const bool svec = p.svec != 0;
+    const int tsb = p.C * 4;
+    const long long cellb = p.cell_stride * 4;
+    const char* vlane = reinterpret_cast<const char*>(p.V) + j * 16;
+    const int ncells = p.N;
+    const int nptiles = (int)p.num_ptiles;
+    const int tstep = (int)gridDim.x * wpb;
+
+    int coff[NCORN];
+#pragma unroll
+    for (int c = 0; c < NCORN; ++c) {
+        coff[c] = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) coff[c] += ((c >> a) & 1) * p.tstride[a];
+    }
+
+    int pt = (int)blockIdx.x * wpb + warp;
+    if (pt >= nptiles) return;
+
+    float gcur[PPL][DIM], gnext[PPL][DIM];
+    auto load_coords = [&](float (&g)[PPL][DIM], int tile) {
+        const long long pt0 = (long long)tile * PTS;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int i = u * 32 + lane;
+            const long long pi = pt0 + i;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) g[u][a] = 0.f;
+            if (i < PTS && pi < p.P) {
+                const float* gp = p.coords + pi * DIM;
+                if (DIM == 2 && p.cvec2) {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(gp));
+                    g[u][0] = t.x; g[u][1] = t.y;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) g[u][a] = __ldg(gp + a);
+                }
+            }
+        }
+    };
+    auto phase1 = [&](const float (&g)[PPL][DIM], int tile, int n, int par) -> bool {
+        const long long pt0 = (long long)tile * PTS;
+        const float off = __ldg(p.offset + n);
+        float4* rb = recbuf + par * WS::REC1;
+        __syncwarp();                               // everyone is done reading this record buffer
+        bool allv = true;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int i = u * 32 + lane;
+            if (i < PTS) {
+                build_jet_record<DIM, ORDER, PTS>(rb, i, g[u], pt0 + i < p.P, off, p);
+                allv = allv && (__float_as_int(rb[i].y) == FULL);
+            }
+        }
+        return __all_sync(0xffffffffu, allv);       // also a warp barrier: records are visible
+    };
+    auto issue = [&](const float4* rec, int st, int n, bool allv) {
+        const char* vsrc = vlane + (long long)n * cellb;
+        const unsigned d0 = gdst + (st & 1) * GS * 512;
+#pragma unroll
+        for (int s = 0; s < PG; ++s) {
+            const float4 hd = rec[PPQ * q + st * PG + s];
+            const int base = __float_as_int(hd.x);
+            const int mask = __float_as_int(hd.y);
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c) {
+                if (allv) {
+                    cp16(d0 + (s * NCORN + c) * 512, vsrc + (long long)(base + coff[c]) * tsb);
+                } else {
+                    const bool valid = (mask >> c) & 1;
+                    cp16z(d0 + (s * NCORN + c) * 512, vsrc + (long long)(valid ? base + coff[c] : 0) * tsb, valid);
+                }
+            }
+        }
+    };
+
+    // ---- prologue
+    load_coords(gcur, pt);
+    bool allv_cur = phase1(gcur, pt, 0, 0);
+    int ptn = pt + tstep;
+    if (ptn < nptiles) load_coords(gnext, ptn);
+    issue(recbuf, 0, 0, allv_cur);
+    cp_async_commit();
+    int par = 0;
+
+    while (pt < nptiles) {
+        float acc[J][PPQ][4];
+#pragma unroll
+        for (int jt = 0; jt < J; ++jt)
+#pragma unroll
+            for (int t = 0; t < PPQ; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[jt][t][k] = 0.f;
+        const bool next_tile = ptn < nptiles;
+
+        for (int n = 0; n < ncells; ++n) {
+            const float4* rec = recbuf + par * WS::REC1;
+            bool allv_next = true;
+#pragma unroll
+            for (int st = 0; st < NST; ++st) {
+                // ---- produce: next stage of this cell, stage 0 of the next cell, or of the next tile
+                if (st + 1 < NST) {
+                    issue(rec, st + 1, n, allv_cur);
+                } else if (n + 1 < ncells) {
+                    allv_next = phase1(gcur, pt, n + 1, par ^ 1);
+                    issue(recbuf + (par ^ 1) * WS::REC1, 0, n + 1, allv_next);
+                } else if (next_tile) {
+                    allv_next = phase1(gnext, ptn, 0, par ^ 1);
+#pragma unroll
+                    for (int u = 0; u < PPL; ++u)
+#pragma unroll
+                        for (int a = 0; a < DIM; ++a) gcur[u][a] = gnext[u][a];
+                    if (ptn + tstep < nptiles) load_coords(gnext, ptn + tstep);
+                    issue(recbuf + (par ^ 1) * WS::REC1, 0, 0, allv_next);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();                 // everything but the group just committed has landed
+
+                // ---- consume stage st
+                const float4* gb = gbuf + (st & 1) * GS * 32;
+#pragma unroll
+                for (int s = 0; s < PG; ++s) {
+                    const int t = st * PG + s;
+                    const int ri = PPQ * q + t;
+#pragma unroll
+                    for (int h = 0; h < CQ; ++h) {
+                        float4 v[4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) v[cc] = gb[(s * NCORN + 4 * h + cc) * 32 + lane];
+#pragma unroll
+                        for (int jt = 0; jt < J; ++jt) {
+                            const float4 k4 = rec[(1 + jt * CQ + h) * PTS + ri];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const float cf = f4get(k4, cc);
+                                acc[jt][t][0] = fmaf(v[cc].x, cf, acc[jt][t][0]);
+                                acc[jt][t][1] = fmaf(v[cc].y, cf, acc[jt][t][1]);
+                                acc[jt][t][2] = fmaf(v[cc].z, cf, acc[jt][t][2]);
+                                acc[jt][t][3] = fmaf(v[cc].w, cf, acc[jt][t][3]);
+                            }
+                        }
+                    }
+                }
+            }
+            par ^= 1;
+            allv_cur = allv_next;
+        }
+
+        // ---- the sums over the cells leave the registers once per tile
+        const long long qp0 = (long long)pt * PTS + PPQ * q;
+#pragma unroll
+        for (int jt = 0; jt < J; ++jt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float tmp[PPQ];
+#pragma unroll
+                for (int t = 0; t < PPQ; ++t) tmp[t] = acc[jt][t][k];
+                row_store<PPQ>(tmp, p.jets + ((long long)jt * p.C + 4 * j + k) * p.P, qp0, p.P, svec);
+            }
+        pt = ptn;
+        ptn += tstep;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------
+// backward (adjoint): acc[n][corner q][c] += sum_jt gjets[jt][c][p] * coef_jt,q(n, p)
+// ---------------------------------------------------------------------------
+template <int DIM, int LSHIFT, int ORDER, int PPQ>
+__global__ void __launch_bounds__(128, (DIM == 2 ? CS_JET_BLOCKS_2D : CS_JET_BLOCKS_3D))
+cs_jet_bwd_kernel(const JetParams p) {
+    using JL = JetLayout<DIM, ORDER>;
+    using WS = JetSmem<DIM, LSHIFT, ORDER, PPQ>;
+    constexpr int NCORN = JL::NCORN;
+    constexpr int CQ = JL::CQ;
+    constexpr int J = JL::J;
+    constexpr int L = 1 << LSHIFT;
+    constexpr int PTS = WS::PTS;
+    constexpr int PPL = (PTS + 31) / 32;
+    constexpr int FULL = (1 << NCORN) - 1;
+
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int q = lane >> LSHIFT;
+    const int j = lane & (L - 1);
+    float4* rec = smem4 + (size_t)warp * WS::TOTAL_BWD;
+
+    const bool svec = p.svec != 0;
+    const int ncells = p.N;
+    const int nptiles = (int)p.num_ptiles;
+    const int tstep = (int)gridDim.x * wpb;
+
+    int coff[NCORN];
+#pragma unroll
+    for (int c = 0; c < NCORN; ++c) {
+        coff[c] = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) coff[c] += ((c >> a) & 1) * p.tstride[a];
+    }
+
+    for (int pt = (int)blockIdx.x * wpb + warp; pt < nptiles; pt += tstep) {
+        const long long pt0 = (long long)pt * PTS;
+        const long long qp0 = pt0 + PPQ * q;
+        // the J x 4 rows of d loss / d jets of this lane's quad: read once, used for all N cells
+        float x[J][PPQ][4];
+#pragma unroll
+        for (int jt = 0; jt < J; ++jt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float tmp[PPQ];
+                row_load<PPQ>(tmp, p.gjets + ((long long)jt * p.C + 4 * j + k) * p.P, qp0, p.P, svec);
+#pragma unroll
+                for (int t = 0; t < PPQ; ++t) x[jt][t][k] = tmp[t];
+            }
+        float g[PPL][DIM];
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int i = u * 32 + lane;
+            const long long pi = pt0 + i;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) g[u][a] = 0.f;
+            if (i < PTS && pi < p.P) {
+                const float* gp = p.coords + pi * DIM;
+                if (DIM == 2 && p.cvec2) {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(gp));
+                    g[u][0] = t.x; g[u][1] = t.y;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) g[u][a] = __ldg(gp + a);
+                }
+            }
+        }
+
+        for (int n = 0; n < ncells; ++n) {
+            const float off = __ldg(p.offset + n);
+            __syncwarp();                           // the previous cell's records are no longer read
+            bool allv = true;
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+                const int i = u * 32 + lane;
+                if (i < PTS) {
+                    build_jet_record<DIM, ORDER, PTS>(rec, i, g[u], pt0 + i < p.P, off, p);
+                    allv = allv && (__float_as_int(rec[i].y) == FULL);
+                }
+            }
+            allv = __all_sync(0xffffffffu, allv);
+            float* adst = p.acc + (long long)n * p.cell_stride + 4 * j;
+#pragma unroll
+            for (int t = 0; t < PPQ; ++t) {
+                const int ri = PPQ * q + t;
+                const float4 hd = rec[ri];
+                const int base = __float_as_int(hd.x);
+                const int mask = allv ? FULL : __float_as_int(hd.y);
+                if (mask == 0) continue;
+#pragma unroll
+                for (int h = 0; h < CQ; ++h) {
+                    float sv[4][4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sv[cc][k] = 0.f;
+#pragma unroll
+                    for (int jt = 0; jt < J; ++jt) {
+                        const float4 k4 = rec[(1 + jt * CQ + h) * PTS + ri];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const float cf = f4get(k4, cc);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) sv[cc][k] = fmaf(x[jt][t][k], cf, sv[cc][k]);
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int c = 4 * h + cc;
+                        if ((mask >> c) & 1)
+                            red_add_v4(adst + (long long)(base + coff[c]) * p.C, sv[cc][0], sv[cc][1], sv[cc][2], sv[cc][3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------
+template <int DIM, int LSHIFT, int ORDER, int PPQ, bool BWD>
+cudaError_t launch_jet_one(const JetParams& p, cudaStream_t stream) {
+    using WS = JetSmem<DIM, LSHIFT, ORDER, PPQ>;
+    auto kern = BWD ? cs_jet_bwd_kernel<DIM, LSHIFT, ORDER, PPQ> : cs_jet_fwd_kernel<DIM, LSHIFT, ORDER, PPQ>;
+    constexpr size_t smem_per_warp = (size_t)(BWD ? WS::TOTAL_BWD : WS::TOTAL_FWD) * sizeof(float4);
+    int warps = 4;
+    while (warps > 1 && warps * smem_per_warp > 72 * 1024) warps >>= 1;
+    const int threads = warps * 32;
+    const size_t smem = warps * smem_per_warp;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    static int occ_cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int& occ = occ_cache[dev];
+    if (occ == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    long long blocks = (p.num_ptiles + warps - 1) / warps;
+    const long long cap = (long long)sms * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return cudaSuccess;
+    kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int DIM> struct JetPPQ { static constexpr int value = (DIM == 2) ? 4 : 2; };
+
+template <int DIM, int LSHIFT>
+cudaError_t launch_jet_variant(int order, bool backward, JetParams& p, cudaStream_t s) {
+    constexpr int PPQ = JetPPQ<DIM>::value;
+    constexpr int PTS = PPQ * (32 >> LSHIFT);
+    p.num_ptiles = (p.P + PTS - 1) / PTS;
+    if (order == 2)
+        return backward ? launch_jet_one<DIM, LSHIFT, 2, PPQ, true>(p, s) : launch_jet_one<DIM, LSHIFT, 2, PPQ, false>(p, s);
+    return backward ? launch_jet_one<DIM, LSHIFT, 1, PPQ, true>(p, s) : launch_jet_one<DIM, LSHIFT, 1, PPQ, false>(p, s);
+}
+
+}  // namespace cs

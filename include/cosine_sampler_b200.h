@@ -125,6 +125,24 @@ int cs_backward_backward_backward(const cs_problem *pb, const float *input, cons
                                   cs_stream gOutggOut, const float *offset, float *gInput,
                                   float *ggOut, void *stream);
 
+/* ---- Fused multi-cell jet operator (not in the reference; SURVEY section 8f ranks 1 + 2) ------------
+ * One gather pass replaces the forward, first-backward (gGrid) and double-backward (gGrid) calls of
+ * modules_2d.py:22-74 for a point set shared by all N cells (test_2d.py:36-38) and the caller's sum
+ * over the cells (test_2d.py:51):
+ *     jets[0]        [C,P] = sum_n sum_q input[n, corner q] * w_q             (cu2d:315-353)
+ *     jets[1+a]      [C,P] = sum_n sum_q input[n, corner q] * dw_q/dg_a       (cu2d:476-503)
+ *     jets[1+dim+a]  [C,P] = sum_n sum_q input[n, corner q] * d2w_q/dg_a^2    (cu2d:694-706; order 2)
+ * a = 0..dim-1 in the order of grid[..., a].  jets is [1 + order*dim, C, P] contiguous, coords [P, dim].
+ * pb->field_layout must be CS_LAYOUT_CHANNEL_LAST (input is [N, T, C]) and C in {4, 8, 16, 32};
+ * pb->grid_stride_n, lanes, small_cell, grad_order are ignored; align_corners is honoured in 2D too. */
+int cs_jet_forward(const cs_problem *pb, int32_t order, const float *input, const float *coords,
+                   const float *offset, float *jets, void *stream);
+/* Adjoint of cs_jet_forward: gInput[n, corner q] += sum_j gJets[j] * coef_j,q  -- the triple-backward
+ * scatters of modules_2d.py:98-111 in one pass.  gInput is channel-last [N, T, C], zero-initialised
+ * by the caller. */
+int cs_jet_backward(const cs_problem *pb, int32_t order, const float *gJets, const float *coords,
+                    const float *offset, float *gInput, void *stream);
+
 /* Staging between the reference layout and the channel-last layout.
  * src [N, C, T] -> dst [N, T, C]   (T = D*H*W) */
 int cs_to_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T, void *stream);

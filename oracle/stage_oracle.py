@@ -277,3 +277,51 @@ def backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, p
         ggO += V * E.view(s.N, 1, s.P)
         s.scatter(gI, idx, inb, go * E.view(s.N, 1, s.P))
     return gI.reshape(input.shape), ggO.reshape(gOut.shape)
+
+
+# ---------------------------------------------------------------------------
+# Jet operator (cosinesampler_b200/jet.py; not in the reference): the same per-corner terms as
+# the four entry points above, summed over the cells and kept per channel.  Pinned in
+# tests/test_stage_oracle.py against forward / backward / backward_backward /
+# backward_backward_backward above (contracting the channels with a random gOut).
+# ---------------------------------------------------------------------------
+def _jet_setup(input, coords, offset, pad, align, kernel, multicell, index_mode, compute_dtype):
+    N = input.shape[0]
+    nd = coords.shape[-1]
+    P = coords.shape[0]
+    grid = coords.reshape((1,) * nd + (P, nd)).expand((N,) + (1,) * (nd - 1) + (P, nd))
+    return _Setup(input, grid, offset, pad, align, kernel, multicell, index_mode, compute_dtype)
+
+
+def jet_forward(input, coords, offset, order=2, pad=0, align=True, kernel=0, multicell=True,
+                index_mode=0, compute_dtype=torch.float64):
+    """jets [1 + order*dim, C, P]: value, d/dg_a, d2/dg_a^2 of sum_n sample(input[n], coords)."""
+    s = _jet_setup(input, coords, offset, pad, align, kernel, multicell, index_mode, compute_dtype)
+    nd = s.nd
+    jets = torch.zeros(1 + order * nd, s.C, s.P, dtype=s.dt)
+    for bits, idx, inb in s.corners():
+        V = s.gather(input, idx, inb)                                   # [N,C,P]
+        jets[0] += (V * s.w(bits).view(s.N, 1, s.P)).sum(0)
+        for a in range(nd):
+            jets[1 + a] += (V * s.d1(bits, a).view(s.N, 1, s.P)).sum(0)
+            if order >= 2:
+                jets[1 + nd + a] += (V * s.d2(bits, a, a).view(s.N, 1, s.P)).sum(0)
+    return jets
+
+
+def jet_backward(gJets, input_shape, coords, offset, order=2, pad=0, align=True, kernel=0,
+                 multicell=True, index_mode=0, compute_dtype=torch.float64):
+    """Adjoint of jet_forward: gInput [N,C,*S]."""
+    proto = torch.zeros(input_shape, dtype=compute_dtype)
+    s = _jet_setup(proto, coords, offset, pad, align, kernel, multicell, index_mode, compute_dtype)
+    nd = s.nd
+    g = gJets.to(s.dt)
+    gI = torch.zeros(s.N, s.C, s.T, dtype=s.dt)
+    for bits, idx, inb in s.corners():
+        coef = g[0].unsqueeze(0) * s.w(bits).view(s.N, 1, s.P)
+        for a in range(nd):
+            coef = coef + g[1 + a].unsqueeze(0) * s.d1(bits, a).view(s.N, 1, s.P)
+            if order >= 2:
+                coef = coef + g[1 + nd + a].unsqueeze(0) * s.d2(bits, a, a).view(s.N, 1, s.P)
+        s.scatter(gI, idx, inb, coef)
+    return gI.reshape(input_shape)

@@ -124,3 +124,52 @@ def test_linear_stage_oracle_equals_grid_sample_with_padding(pad, pname, align):
                              multicell=False, index_mode=2)
         torch.testing.assert_close(gI, rI, rtol=1e-6, atol=1e-6)
         torch.testing.assert_close(gG, rG, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# jet oracle (cosinesampler_b200/jet.py) pinned to the four stage oracles above
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("multicell", [True, False])
+@pytest.mark.parametrize("name,kcode", KERNELS)
+@pytest.mark.parametrize("dim", [2, 3])
+def test_jet_oracle_matches_stage_oracles(dim, name, kcode, multicell):
+    inp, grid, off, gen = _setup(dim, multicell, seed=3, C=4)
+    N, C = inp.shape[:2]
+    P = grid.shape[-2]
+    coords = grid[0].reshape(P, dim)
+    kw = dict(pad=0, align=True, kernel=kcode, multicell=multicell, index_mode=2)
+    jets = so.jet_forward(inp, coords, off, order=2, **kw)
+    assert jets.shape == (1 + 2 * dim, C, P)
+    close = lambda a, b: torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-11)
+
+    # value = F summed over the cells
+    close(jets[0], so.forward(inp, grid, off, **kw).reshape(N, C, P).sum(0))
+    gOut = torch.randn(C, P, generator=gen, dtype=torch.float64)
+    gOutN = gOut.reshape((1, C) + (1,) * (dim - 1) + (P,)).repeat((N,) + (1,) * (dim + 1))
+    # first derivatives: B's gGrid is the contraction of z_a with gOut over the channels
+    _, gG = so.backward(gOutN, inp, grid, off, input_requires_grad=False, **kw)
+    for a in range(dim):
+        close((jets[1 + a] * gOut).sum(0), gG.reshape(N, P, dim)[..., a].sum(0))
+    # pure second derivatives: BB's gGrid with gOutGrid hot on axis a
+    for a in range(dim):
+        hot = torch.zeros(grid.shape, dtype=torch.float64)
+        hot[..., a] = 1.0
+        _, gG2, ggO = so.backward_backward(None, hot, inp, grid, gOutN, off, input_requires_grad=False, **kw)
+        close((jets[1 + dim + a] * gOut).sum(0), gG2.reshape(N, P, dim)[..., a].sum(0))
+        close(jets[1 + a], ggO.reshape(N, C, P).sum(0))          # ggOut of BB = z_a
+
+    # adjoint: each jet's share of jet_backward is the gInput of the matching stage
+    G = torch.randn(jets.shape, generator=gen, dtype=torch.float64)
+    gI = so.jet_backward(G, inp.shape, coords, off, order=2, **kw)
+    rep = lambda t: t.reshape((1, C) + (1,) * (dim - 1) + (P,)).repeat((N,) + (1,) * (dim + 1))
+    want = so.backward(rep(G[0]), inp, grid, off, input_requires_grad=True, **kw)[0]
+    for a in range(dim):
+        hot = torch.zeros(grid.shape, dtype=torch.float64)
+        hot[..., a] = 1.0
+        want = want + so.backward_backward(None, hot, inp, grid, rep(G[1 + a]), off, **kw)[0]
+        want = want + so.backward_backward_backward(inp, grid, rep(G[1 + dim + a]), hot, hot, off, **kw)[0]
+    close(gI, want)
+    # <jets(V), G> == <V, jet_backward(G)>
+    close((jets * G).sum(), (inp * gI).sum())
+    # order 1 is a prefix of order 2
+    close(so.jet_forward(inp, coords, off, order=1, **kw), jets[:1 + dim])
