@@ -14,7 +14,7 @@ EXPORTS = (
     "cs_version", "cs_last_error", "cs_launch_count",
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
-    "cs_jet_forward", "cs_jet_backward",
+    "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step",
 )
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
@@ -36,6 +36,12 @@ class Problem(ctypes.Structure):
         ("lanes", ctypes.c_int32), ("small_cell", ctypes.c_int32),
         ("grad_order", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
+
+
+class PdeResidual(ctypes.Structure):
+    """struct cs_pde_residual"""
+    _fields_ = [("c_u", ctypes.c_float), ("c_u3", ctypes.c_float),
+                ("c1", ctypes.c_float * 3), ("c2", ctypes.c_float * 3)]
 
 
 class Stream3(ctypes.Structure):
@@ -77,6 +83,9 @@ def load():
     lib.cs_jet_forward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
     lib.cs_jet_backward.restype = ctypes.c_int
     lib.cs_jet_backward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
+    lib.cs_pde_head_step.restype = ctypes.c_int
+    lib.cs_pde_head_step.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, ctypes.POINTER(PdeResidual),
+                                     ctypes.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cs_to_channel_last.restype = ctypes.c_int
     lib.cs_to_channel_last.argtypes = [vp, vp, i32, i32, i64, vp]
     lib.cs_from_channel_last.restype = ctypes.c_int

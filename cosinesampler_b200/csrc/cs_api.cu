@@ -10,6 +10,7 @@
 #include "../../include/cosine_sampler_b200.h"
 #include "cs_engine.cuh"
 #include "cs_jet.cuh"
+#include "cs_head.cuh"
 
 namespace cs {
 // one function per (dim, field vector width, log2 lanes) variant, each in its own object file
@@ -22,6 +23,7 @@ CS_DECL(launch_d2_v1_l0) CS_DECL(launch_d3_v1_l0)
 CS_DECLJ(launch_jet_d2_l0) CS_DECLJ(launch_jet_d2_l1) CS_DECLJ(launch_jet_d2_l2) CS_DECLJ(launch_jet_d2_l3)
 CS_DECLJ(launch_jet_d3_l0) CS_DECLJ(launch_jet_d3_l1) CS_DECLJ(launch_jet_d3_l2) CS_DECLJ(launch_jet_d3_l3)
 #undef CS_DECLJ
+cudaError_t launch_head_any(int dim, int C, const HeadParams& p, cudaStream_t s);
 }  // namespace cs
 
 namespace {
@@ -387,6 +389,32 @@ int cs_jet_forward(const cs_problem* pb, int32_t order, const float* input, cons
 int cs_jet_backward(const cs_problem* pb, int32_t order, const float* gJets, const float* coords,
                     const float* offset, float* gInput, void* stream) {
     return jet_run(pb, order, true, nullptr, gInput, coords, offset, nullptr, gJets, stream);
+}
+
+int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float* jets, const float* W1, const float* b1,
+                     const float* w2, const float* b2, const cs_pde_residual* res, float scale,
+                     float* gJets, float* gW1, float* gb1, float* gw2, float* gb2, float* loss_sum,
+                     float* f_out, void* stream) {
+    if (dim != 2 && dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", dim);
+    if (!(C == 4 || C == 8 || C == 16 || C == 32))
+        return fail(CS_EUNSUPPORTED, "cs_pde_head_step needs C in {4, 8, 16, 32}, got %d", C);
+    if (P < 0) return fail(CS_EINVAL, "negative size");
+    if (P == 0) return 0;
+    if (!jets || !W1 || !b1 || !w2 || !b2 || !res || !gJets || !gW1 || !gb1 || !gw2 || !gb2 || !loss_sum)
+        return fail(CS_EINVAL, "cs_pde_head_step: NULL pointer");
+    cs::HeadParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = P; p.jets = jets; p.gjets = gJets;
+    p.W1 = W1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+    p.gW1 = gW1; p.gb1 = gb1; p.gw2 = gw2; p.gb2 = gb2; p.loss_sum = loss_sum; p.f_out = f_out;
+    p.c_u = res->c_u; p.c_u3 = res->c_u3;
+    for (int a = 0; a < 3; ++a) { p.c1[a] = res->c1[a]; p.c2[a] = res->c2[a]; }
+    p.scale = scale;
+    p.vec = (P % 4 == 0) && aligned16(jets) && aligned16(gJets);
+    cudaError_t e = cs::launch_head_any(dim, C, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pde head kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }
 
 int cs_to_channel_last(const float* src, float* dst, int32_t N, int32_t C, int64_t T, void* stream) {

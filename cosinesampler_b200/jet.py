@@ -25,6 +25,9 @@ scatters of `modules_2d.py:98-111` in one kernel).  Gradients w.r.t. `coords` ar
 Needs C in {4, 8, 16, 32}; `align_corners` is honoured in 2D as well (the reference's 2D forward
 ignores it, cu2d:307-308 -- with the default `True` there is no difference).
 """
+import ctypes
+import math
+
 import torch
 
 from . import _lib, ops
@@ -80,8 +83,10 @@ def jet_forward(input, coords, offset, padding_mode, align_corners, kernel, mult
     return jets
 
 
-def jet_backward(gJets, input, coords, offset, padding_mode, align_corners, kernel, multicell, order=2):
-    """gInput [N,C,(D,)H,W] = adjoint of jet_forward applied to gJets (cs_jet_backward)."""
+def jet_backward_into(acc, gJets, input, coords, offset, padding_mode, align_corners, kernel, multicell,
+                      order=2):
+    """acc [N,T,C] (channel-last, caller-initialised) += adjoint of jet_forward applied to gJets.
+    Several point chunks can share one accumulator (`new_accumulator` / `finish_accumulator`)."""
     dim = _check_args(input, coords, order)
     ops._check(offset, "offset")
     ops._check(gJets, "gJets", contiguous=False)
@@ -90,14 +95,29 @@ def jet_backward(gJets, input, coords, offset, padding_mode, align_corners, kern
     if tuple(gJets.shape) != (1 + order * dim, C, P):
         raise RuntimeError("gJets must be %s, got %s" % ((1 + order * dim, C, P), tuple(gJets.shape)))
     gJets = gJets.contiguous()
-    acc = ops._new_accumulator(input, _lib.LAYOUT_CHANNEL_LAST)
     pb = _problem(input, coords, padding_mode, align_corners, kernel, multicell)
     nbytes = jet_bytes(dim, N, C, P, input[0, 0].numel() if N and C else 0, order)
     with ops._on_device(input.device), ops._timed("JET%dd[bwd]" % dim, nbytes, input.device):
         rc = _lib.load().cs_jet_backward(pb, order, gJets.data_ptr(), coords.data_ptr(), offset.data_ptr(),
                                          acc.data_ptr(), ops._cur_stream(input.device))
     _lib.check(rc, "cs_jet_backward")
+
+
+def new_accumulator(input):
+    """Zeroed channel-last gInput accumulator [N,T,C] for `jet_backward_into`."""
+    return ops._new_accumulator(input, _lib.LAYOUT_CHANNEL_LAST)
+
+
+def finish_accumulator(acc, input):
+    """Channel-last accumulator -> gInput in the reference layout [N,C,(D,)H,W]."""
     return ops._finish_accumulator(acc, input, _lib.LAYOUT_CHANNEL_LAST)
+
+
+def jet_backward(gJets, input, coords, offset, padding_mode, align_corners, kernel, multicell, order=2):
+    """gInput [N,C,(D,)H,W] = adjoint of jet_forward applied to gJets (cs_jet_backward)."""
+    acc = new_accumulator(input)
+    jet_backward_into(acc, gJets, input, coords, offset, padding_mode, align_corners, kernel, multicell, order)
+    return finish_accumulator(acc, input)
 
 
 def _make_jet_function(dim):
@@ -177,4 +197,150 @@ def jet_mlp(head, jets, dim, order=2):
     return u, u_a, u_aa
 
 
-__all__ = ["SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_mlp", "jet_bytes"]
+# ---------------------------------------------------------------------------
+# Fused head + residual (cs_pde_head_step) and the fused training step
+# ---------------------------------------------------------------------------
+def residual_coefficients(residual, dim, k2=math.pi ** 2):
+    """f = c_u u + c_u3 u^3 + sum_a (c1[a] u_a + c2[a] u_aa) for the residuals of `chain.pde_loss`
+    (a in grid-channel order x, y(, z)), or pass a dict with those keys for another residual."""
+    r = _lib.PdeResidual()
+    if isinstance(residual, dict):
+        r.c_u, r.c_u3 = float(residual.get("c_u", 0.0)), float(residual.get("c_u3", 0.0))
+        for a in range(dim):
+            r.c1[a] = float(residual.get("c1", [0.0] * dim)[a])
+            r.c2[a] = float(residual.get("c2", [0.0] * dim)[a])
+        return r
+    if residual == "t2d":                            # test_2d.py:221
+        if dim != 2:
+            raise ValueError("the t2d residual is two-dimensional")
+        r.c_u, r.c_u3 = -5.0, 5.0
+        r.c1[1] = 2.0
+        r.c2[0] = -0.0001
+    elif residual in ("helmholtz", "laplace"):       # README Helmholtz; test_3d.py:270
+        r.c_u = float(k2) if residual == "helmholtz" else 1.0
+        for a in range(dim):
+            r.c2[a] = 1.0
+    else:
+        raise ValueError(residual)
+    return r
+
+
+def _head_params(head, C):
+    """(W1 [16,C], b1 [16], w2 [1,16], b2 [1]) of a Linear(C,16)-Tanh-Linear(16,1) head (test_2d.py:42-47)."""
+    layers = list(head)
+    ok = (len(layers) == 3 and isinstance(layers[0], torch.nn.Linear) and isinstance(layers[1], torch.nn.Tanh)
+          and isinstance(layers[2], torch.nn.Linear) and layers[0].in_features == C
+          and layers[0].out_features == 16 and layers[2].in_features == 16 and layers[2].out_features == 1
+          and layers[0].bias is not None and layers[2].bias is not None)
+    if not ok:
+        raise NotImplementedError("the fused head is Linear(C,16)-Tanh-Linear(16,1) with biases; use "
+                                  "jet_mlp (torch ops) for other heads")
+    ps = (layers[0].weight, layers[0].bias, layers[2].weight, layers[2].bias)
+    for t in ps:
+        ops._check(t, "head parameter")
+    return ps
+
+
+def pde_head_step(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=1.0, in_place=False,
+                  want_f=False):
+    """One launch of cs_pde_head_step on jets [1+2*dim, C, P]: returns
+    (sum_p f^2 as a 0-dim tensor (unscaled), gJets, (gW1, gb1, gw2, gb2), f or None) where the
+    gradients are those of  scale * sum_p f^2.  in_place=True overwrites `jets` with gJets."""
+    ops._check(jets, "jets")
+    J, C, P = jets.shape
+    if J != 1 + 2 * dim:
+        raise RuntimeError("jets must be [1+2*dim, C, P], got %s" % (tuple(jets.shape),))
+    W1, b1, w2, b2 = _head_params(head, C)
+    res = residual_coefficients(residual, dim, k2)
+    gJets = jets if in_place else torch.empty_like(jets)
+    # one zeroed buffer for every accumulated output: gW1 | gb1 | gw2 | gb2 | loss_sum
+    buf = torch.zeros(16 * C + 34, dtype=jets.dtype, device=jets.device)
+    f = torch.empty(P, dtype=jets.dtype, device=jets.device) if want_f else None
+    base = buf.data_ptr()
+    nbytes = 4 * 2 * J * C * P
+    with ops._on_device(jets.device), ops._timed("HEAD%dd" % dim, nbytes, jets.device):
+        rc = _lib.load().cs_pde_head_step(
+            dim, C, P, jets.data_ptr(), W1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            ctypes.byref(res), float(scale), gJets.data_ptr(), base, base + 4 * 16 * C,
+            base + 4 * (16 * C + 16), base + 4 * (16 * C + 32), base + 4 * (16 * C + 33),
+            f.data_ptr() if f is not None else None, ops._cur_stream(jets.device))
+    _lib.check(rc, "cs_pde_head_step")
+    grads = (buf[:16 * C].view(16, C), buf[16 * C:16 * C + 16], buf[16 * C + 16:16 * C + 32].view(1, 16),
+             buf[16 * C + 32:16 * C + 33])
+    return buf[16 * C + 33], gJets, grads, f
+
+
+class PdeHeadLoss(torch.autograd.Function):
+    """loss = scale * sum_p f_p^2 as a differentiable (once) function of the jets and the head
+    parameters: forward runs the fused kernel, which already produces every gradient."""
+
+    @staticmethod
+    def forward(ctx, jets, W1, b1, w2, b2, head, dim, residual, k2, scale):
+        loss_sum, gJets, grads, _ = pde_head_step(jets.detach(), head, dim, residual, k2, scale)
+        ctx.save_for_backward(gJets, *grads)
+        return loss_sum * scale
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gl):
+        gJets, gW1, gb1, gw2, gb2 = ctx.saved_tensors
+        return gJets * gl, gW1 * gl, gb1 * gl, gw2 * gl, gb2 * gl, None, None, None, None, None
+
+
+def pde_head_loss(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=None):
+    """mean_p f_p^2 (scale defaults to 1/P), differentiable w.r.t. `jets` and the head parameters."""
+    if scale is None:
+        scale = 1.0 / max(1, jets.shape[-1])
+    W1, b1, w2, b2 = _head_params(head, jets.shape[1])
+    return PdeHeadLoss.apply(jets, W1, b1, w2, b2, head, dim, residual, k2, scale)
+
+
+def _add_grad(param, g, owned=False):
+    if param.grad is None:
+        param.grad = g if owned else g.clone()
+    else:
+        param.grad.add_(g)
+
+
+def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
+                   align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0):
+    """One PIXEL training step without autograd: for every chunk of points
+        jets  = cs_jet_forward(cells, coords)                 (one gather pass)
+        gJets = cs_pde_head_step(jets, head)                  (head, residual, loss and all gradients)
+        acc  += cs_jet_backward(gJets)                        (one scatter pass)
+    then `cells.grad` and the head parameters' `.grad` are accumulated, exactly what
+    `chain.training_step` does with `loss.backward()`.  `cells` is staged channel-last once and all
+    chunks scatter into one channel-last accumulator.  coords: [P, dim].  Returns the loss
+    (loss_scale * mean_p f^2) as a 0-dim tensor; nothing synchronises with the host."""
+    dim = coords.shape[1]
+    _check_args(cells, coords, 2)
+    pm = padding_mode_enum(padding_mode)
+    kn = _require_kernel(_kernel_enum(kernel, "bilinear" if dim == 2 else "trilinear"), kernel)
+    P = coords.shape[0]
+    C = cells.shape[1]
+    W1, b1, w2, b2 = _head_params(head, C)
+    chunk = P if not chunk else min(chunk, P)
+    with torch.no_grad():
+        cells_d = cells.detach()
+        offset = cell_offsets(cells.shape[0], multicell, cells.device)
+        staged = ops.stage(cells_d)
+        acc = new_accumulator(cells_d)
+        loss = None
+        pgrads = None
+        for s in range(0, P, chunk):
+            xy = coords[s:s + chunk]
+            jets = jet_forward(cells_d, xy, offset, pm, align_corners, kn, multicell, 2, staged=staged)
+            loss_sum, gJets, grads, _ = pde_head_step(jets, head, dim, residual, k2, loss_scale / P, in_place=True)
+            jet_backward_into(acc, gJets, cells_d, xy, offset, pm, align_corners, kn, multicell, 2)
+            loss = loss_sum if loss is None else loss + loss_sum
+            pgrads = grads if pgrads is None else tuple(a + b for a, b in zip(pgrads, grads))
+        if cells.requires_grad:
+            _add_grad(cells, finish_accumulator(acc, cells_d), owned=True)
+        for prm, g in zip((W1, b1, w2, b2), pgrads):
+            if prm.requires_grad:
+                _add_grad(prm, g)
+        return loss * (loss_scale / P)
+
+
+__all__ = ["SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
+           "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "residual_coefficients"]

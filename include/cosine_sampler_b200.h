@@ -143,6 +143,24 @@ int cs_jet_forward(const cs_problem *pb, int32_t order, const float *input, cons
 int cs_jet_backward(const cs_problem *pb, int32_t order, const float *gJets, const float *coords,
                     const float *offset, float *gInput, void *stream);
 
+/* ---- Fused PDE-residual head on jets (PIXEL caller glue; not in the reference) ---------------------
+ * The head of the reference's scripts, Linear(C,16)-Tanh-Linear(16,1) (test_2d.py:42-47), applied to the
+ * jets of cs_jet_forward in second-order Taylor mode, a residual
+ *     f = c_u u + c_u3 u^3 + sum_a (c1[a] u_a + c2[a] u_aa)
+ * (test_2d.py:221: c1[1] = 2, c_u3 = 5, c_u = -5, c2[0] = -1e-4; test_3d.py:270: c_u = 1, c2[a] = 1;
+ * Helmholtz: c_u = k^2, c2[a] = 1), and in the same pass the gradients of scale * sum_p f^2 with respect
+ * to the jets (gJets [1+2*dim, C, P], may alias jets) and the head parameters (gW1 [16,C], gb1 [16],
+ * gw2 [16], gb2 [1]: accumulated with +=, as is loss_sum [1] += sum_p f^2, unscaled).  f_out [P] nullable. */
+typedef struct cs_pde_residual {
+    float c_u, c_u3;
+    float c1[3];
+    float c2[3];
+} cs_pde_residual;
+int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float *jets, const float *W1, const float *b1,
+                     const float *w2, const float *b2, const cs_pde_residual *res, float scale,
+                     float *gJets, float *gW1, float *gb1, float *gw2, float *gb2, float *loss_sum,
+                     float *f_out, void *stream);
+
 /* Staging between the reference layout and the channel-last layout.
  * src [N, C, T] -> dst [N, T, C]   (T = D*H*W) */
 int cs_to_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T, void *stream);

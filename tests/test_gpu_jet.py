@@ -190,3 +190,101 @@ def test_jet_api_errors(cuda):
     # empty point set
     out = jet.SamplerJet2d.apply(torch.rand(2, 8, 8, 8, device=cuda), torch.rand(0, 2, device=cuda))
     assert out.shape == (5, 8, 0)
+
+
+# ---------------------------------------------------------------------------
+# fused head + residual kernel (cs_pde_head_step) and the fused training step
+# ---------------------------------------------------------------------------
+def _torch_head_reference(jets64, head64, dim, residual, k2, scale):
+    """loss, f and every gradient by torch autograd over jet_mlp in fp64 on the CPU."""
+    from cosinesampler_b200.chain import _residual
+    from cosinesampler_b200.jet import jet_mlp
+    jets64 = jets64.clone().requires_grad_(True)
+    u, first, second = jet_mlp(head64, jets64, dim)
+    f = _residual(u, first, second, residual, k2)
+    loss_sum = (f ** 2).sum()
+    params = [head64[0].weight, head64[0].bias, head64[2].weight, head64[2].bias]
+    grads = torch.autograd.grad(loss_sum * scale, [jets64] + params)
+    return loss_sum.detach(), f.detach().reshape(-1), grads[0], grads[1:]
+
+
+@pytest.mark.parametrize("residual", ["helmholtz", "t2d", "laplace"])
+@pytest.mark.parametrize("C", [4, 8, 16, 32])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_pde_head_step_matches_torch_autograd(cuda, dim, C, residual):
+    from cosinesampler_b200 import jet
+    if residual == "t2d" and dim == 3:
+        pytest.skip("t2d is a 2D residual")
+    gen = torch.Generator().manual_seed(7 * C + dim)
+    J = 1 + 2 * dim
+    for P in (1003, 4096):
+        jets = torch.randn(J, C, P, generator=gen)
+        jets[1:1 + dim] *= 3.0
+        jets[1 + dim:] *= 9.0
+        head32 = make_head(C, seed=4).to(cuda)
+        head64 = make_head(C, seed=4, dtype=torch.float64)
+        scale = 0.37 / P
+        k2 = 9.8696
+        loss_sum, gJets, grads, f = jet.pde_head_step(jets.to(cuda), head32, dim, residual, k2, scale, want_f=True)
+        r_loss, r_f, r_gJets, r_grads = _torch_head_reference(jets.double(), head64, dim, residual, k2, scale)
+        what = "head %dD C=%d P=%d %s " % (dim, C, P, residual)
+        assert_close_scaled(f, r_f, what + "f")
+        assert_close_scaled(loss_sum, r_loss, what + "loss_sum", rtol=1e-5)
+        assert_close_scaled(gJets, r_gJets, what + "gJets", atol_scale=2e-6)
+        for name, a, b in zip(("gW1", "gb1", "gw2", "gb2"), grads, r_grads):
+            assert_close_scaled(a, b, what + name, rtol=2e-5, atol_scale=2e-5)
+        # in place: the gradient overwrites the jets
+        buf = jets.to(cuda)
+        _, g2, _, _ = jet.pde_head_step(buf, head32, dim, residual, k2, scale, in_place=True)
+        assert g2.data_ptr() == buf.data_ptr()
+        assert torch.equal(g2, gJets)
+
+
+def test_fused_pde_step_equals_dropin_training_step(cuda):
+    """jet.fused_pde_step (3 launches per chunk, no autograd) == chain.training_step through the
+    drop-in operator (14 launches + torch autograd): loss, cells.grad, head grads."""
+    from cosinesampler_b200 import jet
+    from cosinesampler_b200.chain import training_step
+    from cosine_sampler_2d import CosineSampler2d
+    from cosine_sampler_3d import CosineSampler3d
+    for dim, shape, kernel, residual, D in ((2, (4, 16, 64, 64), "cosine", "helmholtz", CosineSampler2d),
+                                            (2, (4, 16, 64, 64), "cosine", "t2d", CosineSampler2d),
+                                            (3, (4, 16, 16, 16, 16), "smooth-step", "laplace", CosineSampler3d)):
+        gen = torch.Generator().manual_seed(11 + dim)
+        P = 8192
+        cells0 = torch.rand(shape, generator=gen)
+        cols = [(torch.rand(P, 1, generator=gen) * 2 - 1).to(cuda) for _ in range(dim)]
+        coords = torch.cat(cols, -1).contiguous()
+        res = {}
+        for mode in ("dropin", "fused", "fused_chunked", "autograd_head"):
+            cells = torch.nn.Parameter(cells0.clone().to(cuda))
+            head = make_head(shape[1], seed=3).to(cuda)
+            if mode == "dropin":
+                loss = training_step(lambda c, g: D.apply(c, g, "zeros", True, kernel, True), cells, cols, head,
+                                     residual)
+            elif mode == "autograd_head":
+                S = jet.SamplerJet2d if dim == 2 else jet.SamplerJet3d
+                jets = S.apply(cells, coords, "zeros", True, kernel, True)
+                loss = jet.pde_head_loss(jets, head, dim, residual)
+                loss.backward()
+            else:
+                loss = jet.fused_pde_step(cells, coords, head, residual, kernel=kernel,
+                                          chunk=3000 if mode == "fused_chunked" else None)
+            res[mode] = (loss.detach(), cells.grad, [p.grad for p in head.parameters()])
+        for mode in ("fused", "fused_chunked", "autograd_head"):
+            what = "%dD %s %s " % (dim, residual, mode)
+            assert_close_scaled(res[mode][0], res["dropin"][0], what + "loss", rtol=1e-4)
+            assert_close_scaled(res[mode][1], res["dropin"][1], what + "cells.grad", rtol=1e-4, atol_scale=2e-5)
+            for a, b in zip(res[mode][2], res["dropin"][2]):
+                assert_close_scaled(a, b, what + "head grad", rtol=1e-4, atol_scale=2e-5)
+
+
+def test_fused_head_rejects_other_heads(cuda):
+    from cosinesampler_b200 import jet
+    jets = torch.rand(5, 16, 64, device=cuda)
+    wide = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 1)).to(cuda)
+    with pytest.raises(NotImplementedError):
+        jet.pde_head_step(jets, wide, 2)
+    # jet_mlp (torch ops) takes any Linear/Tanh stack
+    u, first, second = jet.jet_mlp(wide, jets, 2)
+    assert u.shape == (64, 1) and len(first) == 2 and len(second) == 2

@@ -72,6 +72,19 @@ def main():
             param.grad = None
             return training_step(lambda c, g: D.apply(c, g, "zeros", True, kernel, True), param, cols, head,
                                  residual)
+        xy = torch.cat(cols, -1).contiguous()
+
+        def step_fused():
+            param.grad = None
+            return jet.fused_pde_step(param, xy, head, residual, kernel=kernel)
+        jets_t = jet.jet_forward(cells, xy, off, 0, True, kn, True, 2, staged=staged)
+        th = timeit(lambda: jet.pde_head_step(jets_t, head, dim, residual, scale=1.0 / Pstep))
+        hb = 4 * 2 * jets_t.numel()
+        print(json.dumps({"config": name, "kernel": "HEAD%dd (+memset)" % dim, "points": Pstep, "ms": th,
+                          "GBps": hb / th / 1e6, "frac": hb / th / 1e6 / PEAK, "bytes": hb}), flush=True)
+        lf = float(step_fused())
+        gf = param.grad.clone()
+        tf = timeit(step_fused, iters=20, warm=5)
         lj = float(step_jet())
         gj = param.grad.clone()
         ld = float(step_dropin())
@@ -79,9 +92,11 @@ def main():
         tj = timeit(step_jet, iters=10, warm=3)
         td = timeit(step_dropin, iters=10, warm=3)
         print(json.dumps({"config": name, "points": Pstep, "ms_step_jet": tj, "ms_step_dropin": td,
-                          "speedup": td / tj, "points_per_s_jet": Pstep / tj * 1e3,
+                          "ms_step_fused": tf, "points_per_s_fused": Pstep / tf * 1e3,
+                          "loss_fused": lf, "speedup_fused_vs_dropin": td / tf, "speedup": td / tj, "points_per_s_jet": Pstep / tj * 1e3,
                           "points_per_s_dropin": Pstep / td * 1e3, "loss_jet": lj, "loss_dropin": ld,
-                          "max_abs_diff_cells_grad_over_max": float((gj - gd).abs().max() / gd.abs().max())}),
+                          "max_abs_diff_cells_grad_over_max": float((gj - gd).abs().max() / gd.abs().max()),
+                          "max_abs_diff_cells_grad_fused_over_max": float((gf - gd).abs().max() / gd.abs().max())}),
               flush=True)
 
 
