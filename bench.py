@@ -182,6 +182,13 @@ def run_ours(args):
     coords_pinned = coords_host.pin_memory()
     coords_dev = coords_host.to(device)
     stepper = dp.PointShardedStep(sampler, cells, head, residual=residual, chunk=chunk)
+    from cosinesampler_b200 import jet
+    fused_kw = dict(kernel=kernel, multicell=True)
+    fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=chunk, fused=fused_kw)
+
+    def fused_resident():
+        fstepper.zero_grad()
+        return fstepper.step(coords_dev, total)
 
     def step_resident():
         stepper.zero_grad()
@@ -221,6 +228,36 @@ def run_ours(args):
             acc = loss if acc is None else acc + loss
         dp.allreduce_grads(stepper.params())
         loss_host.copy_(acc.reshape(1), non_blocking=True)               # D2H of the step's result
+        cur.synchronize()
+        return loss_host
+
+    def fused_e2e():
+        """The fused step from HOST buffers, same copy pipeline as step_e2e."""
+        fstepper.zero_grad()
+        nloc = coords_pinned.shape[0]
+        spans = [(s0, min(nloc, s0 + chunk)) for s0 in range(0, nloc, chunk)]
+        cur = torch.cuda.current_stream()
+
+        def fetch(span):
+            with torch.cuda.stream(copy_stream):
+                t = coords_pinned[span[0]:span[1]].to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
+
+        fs = jet.FusedPdeStep(cells, head, residual, kernel=kernel, multicell=True)
+        fs.begin()
+        nxt = fetch(spans[0])
+        for i, span in enumerate(spans):
+            t, ev = nxt
+            if i + 1 < len(spans):
+                nxt = fetch(spans[i + 1])
+            cur.wait_event(ev)
+            t.record_stream(cur)
+            fs.add(t, 1.0 / float(total))
+        loss = fs.finish()
+        dp.allreduce_grads(fstepper.params())
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
         cur.synchronize()
         return loss_host
 
@@ -265,6 +302,24 @@ def run_ours(args):
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- the opt-in fused jet path (jet.FusedPdeStep), same inputs, same outputs
+    for _ in range(args.warmup):
+        fused_resident()
+    barrier()
+    fprof = StageProfiler()
+    ops.profiler = fprof
+    n0 = _lib.launch_count()
+    ms_f = timed(fused_resident, args.steps)
+    flaunches = _lib.launch_count() - n0
+    ops.profiler = None
+    floss_t = fused_resident().detach().clone()
+    if world > 1:
+        dist.all_reduce(floss_t)
+    floss_val = float(floss_t.item())
+    for _ in range(max(1, min(args.warmup, 2))):
+        fused_e2e()
+    ms_f_e2e = timed(fused_e2e, args.steps)
 
     if rank != 0:
         if world > 1:
@@ -313,6 +368,32 @@ def run_ours(args):
                    for k, v in sorted(stage.items())},
         "loss": loss_val,
         "index_mode": ops.get_index_mode(),
+    }
+    fstage = fprof.summary()
+    ftop = max(fstage, key=lambda k: fstage[k]["ms_total"]) if fstage else None
+    fchain_gbs = chain_bytes * args.steps / (ms_f * 1e-3) / 1e9 / world
+    out["fused"] = {
+        "api": "cosinesampler_b200.jet.FusedPdeStep (opt-in; SURVEY 8f ranks 1+2): jets in one gather pass, "
+               "head + residual + gradients in one kernel, one scatter pass; same loss and gradients",
+        "value": total * args.steps / (ms_f * 1e-3), "unit": "points/s", "ms_per_step": ms_f / args.steps,
+        "e2e": {"value": total * args.steps / (ms_f_e2e * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_f_e2e / args.steps},
+        "gpu_launches": int(flaunches), "loss": floss_val,
+        "speedup_vs_dropin": ms / ms_f,
+        "stages": {k: {"launches": v["launches"], "ms_avg": round(v["ms_avg"], 4),
+                       "GBps": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9, 1),
+                       "frac": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9 / peak, 4)}
+                   for k, v in sorted(fstage.items())},
+        "roofline": None if not ftop else {
+            "kernel": ftop, "bound": "hbm", "unit": "GB/s", "peak": peak,
+            "achieved": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9, 1),
+            "frac": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9 / peak, 4),
+            "bytes_per_launch": fstage[ftop]["bytes_per_launch"], "ms_avg": round(fstage[ftop]["ms_avg"], 4),
+            "share_of_step": round(fstage[ftop]["ms_total"] / ms_f, 4)},
+        "chain_roofline": {"note": "the reference formulation's minimal bytes per step (BASELINE.md section 3) "
+                                   "over the fused step's time", "achieved": round(fchain_gbs, 1),
+                           "peak": peak, "unit": "GB/s per GPU", "frac": round(fchain_gbs / peak, 4)},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample, repeats=2)

@@ -47,9 +47,13 @@ class PointShardedStep:
     gradients.  loss_scale = shard/total makes the summed gradient the gradient of the
     mean over *all* points."""
 
-    def __init__(self, sampler, cells, head, residual="helmholtz", chunk=None, group=None):
+    def __init__(self, sampler, cells, head, residual="helmholtz", chunk=None, group=None, fused=None):
+        """fused: None = `sampler` is a drop-in operator driven through `chain.training_step`
+        (nested autograd, the reference's call pattern); a dict of `jet.fused_pde_step` keyword
+        arguments (kernel=..., multicell=...) = the fused jet path (`sampler` is ignored)."""
         self.sampler, self.cells, self.head = sampler, cells, head
         self.residual, self.chunk, self.group = residual, chunk, group
+        self.fused = fused
 
     def params(self):
         return [self.cells] + list(self.head.parameters())
@@ -59,6 +63,13 @@ class PointShardedStep:
             p.grad = None
 
     def step(self, local_coords, total_points):
+        if self.fused is not None:
+            from .jet import fused_pde_step
+            xy = local_coords if torch.is_tensor(local_coords) else torch.cat(list(local_coords), -1)
+            loss = fused_pde_step(self.cells, xy.contiguous(), self.head, self.residual, chunk=self.chunk,
+                                  loss_scale=xy.shape[0] / float(total_points), **self.fused)
+            allreduce_grads(self.params(), self.group)
+            return loss
         from .chain import training_step
         local = local_coords[0].shape[0]
         loss = training_step(self.sampler, self.cells, local_coords, self.head, self.residual,

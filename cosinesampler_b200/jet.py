@@ -302,45 +302,86 @@ def _add_grad(param, g, owned=False):
         param.grad.add_(g)
 
 
+class FusedPdeStep:
+    """A PIXEL training step without autograd, fed chunk by chunk:
+
+        step = FusedPdeStep(cells, head, residual="helmholtz", kernel="cosine")
+        step.begin()                      # stage `cells` channel-last once, zero one accumulator
+        for xy in chunks:                 # [p, dim] each
+            step.add(xy, 1.0 / P_total)   # jets -> head/residual/gradients -> scatter: 3 launches
+        loss = step.finish()              # cells.grad, head .grad accumulated; 0-dim loss tensor
+
+    which is what `chain.training_step` does with `loss.backward()` through the drop-in operator
+    (14 operator launches and ~200 torch kernels per chunk).  Nothing synchronises with the host."""
+
+    def __init__(self, cells, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
+                 align_corners=True, kernel="cosine", multicell=True):
+        ops._check(cells, "input")
+        self.dim = cells.dim() - 2
+        if self.dim not in (2, 3):
+            raise RuntimeError("expected cells [N,C,(D,)H,W], got %s" % (tuple(cells.shape),))
+        self.cells, self.head = cells, head
+        self.residual, self.k2 = residual, k2
+        self.pm = padding_mode_enum(padding_mode)
+        self.kn = _require_kernel(_kernel_enum(kernel, "bilinear" if self.dim == 2 else "trilinear"), kernel)
+        self.align_corners, self.multicell = align_corners, multicell
+        self.params = _head_params(head, cells.shape[1])
+        self._live = False
+
+    def begin(self):
+        with torch.no_grad():
+            self.cells_d = self.cells.detach()
+            self.offset = cell_offsets(self.cells.shape[0], self.multicell, self.cells.device)
+            self.staged = ops.stage(self.cells_d)
+            self.acc = new_accumulator(self.cells_d)
+        self.loss, self.pgrads, self._live = None, None, True
+
+    def add(self, xy, scale):
+        """One chunk of points xy [p, dim]; its loss contribution is scale * sum_p f^2."""
+        if not self._live:
+            raise RuntimeError("FusedPdeStep.add before begin()")
+        _check_args(self.cells_d, xy, 2)
+        if xy.shape[1] != self.dim:
+            raise RuntimeError("coords must be [p, %d], got %s" % (self.dim, tuple(xy.shape)))
+        with torch.no_grad():
+            a = (self.pm, self.align_corners, self.kn, self.multicell, 2)
+            jets = jet_forward(self.cells_d, xy, self.offset, *a, staged=self.staged)
+            loss_sum, gJets, grads, _ = pde_head_step(jets, self.head, self.dim, self.residual, self.k2, scale,
+                                                      in_place=True)
+            jet_backward_into(self.acc, gJets, self.cells_d, xy, self.offset, *a)
+            part = loss_sum * scale
+            self.loss = part if self.loss is None else self.loss + part
+            self.pgrads = grads if self.pgrads is None else tuple(x + y for x, y in zip(self.pgrads, grads))
+
+    def finish(self):
+        if not self._live:
+            raise RuntimeError("FusedPdeStep.finish before begin()")
+        self._live = False
+        with torch.no_grad():
+            if self.cells.requires_grad:
+                _add_grad(self.cells, finish_accumulator(self.acc, self.cells_d), owned=True)
+            if self.pgrads is not None:
+                for prm, g in zip(self.params, self.pgrads):
+                    if prm.requires_grad:
+                        _add_grad(prm, g)
+            loss = self.loss if self.loss is not None else torch.zeros((), device=self.cells.device)
+        self.acc = self.staged = self.pgrads = self.loss = None
+        return loss
+
+
 def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
                    align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0):
-    """One PIXEL training step without autograd: for every chunk of points
-        jets  = cs_jet_forward(cells, coords)                 (one gather pass)
-        gJets = cs_pde_head_step(jets, head)                  (head, residual, loss and all gradients)
-        acc  += cs_jet_backward(gJets)                        (one scatter pass)
-    then `cells.grad` and the head parameters' `.grad` are accumulated, exactly what
-    `chain.training_step` does with `loss.backward()`.  `cells` is staged channel-last once and all
-    chunks scatter into one channel-last accumulator.  coords: [P, dim].  Returns the loss
-    (loss_scale * mean_p f^2) as a 0-dim tensor; nothing synchronises with the host."""
-    dim = coords.shape[1]
-    _check_args(cells, coords, 2)
-    pm = padding_mode_enum(padding_mode)
-    kn = _require_kernel(_kernel_enum(kernel, "bilinear" if dim == 2 else "trilinear"), kernel)
+    """`FusedPdeStep` over coords [P, dim] in chunks of `chunk` points: accumulates `cells.grad` and the
+    head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor."""
+    step = FusedPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell)
     P = coords.shape[0]
-    C = cells.shape[1]
-    W1, b1, w2, b2 = _head_params(head, C)
-    chunk = P if not chunk else min(chunk, P)
-    with torch.no_grad():
-        cells_d = cells.detach()
-        offset = cell_offsets(cells.shape[0], multicell, cells.device)
-        staged = ops.stage(cells_d)
-        acc = new_accumulator(cells_d)
-        loss = None
-        pgrads = None
-        for s in range(0, P, chunk):
-            xy = coords[s:s + chunk]
-            jets = jet_forward(cells_d, xy, offset, pm, align_corners, kn, multicell, 2, staged=staged)
-            loss_sum, gJets, grads, _ = pde_head_step(jets, head, dim, residual, k2, loss_scale / P, in_place=True)
-            jet_backward_into(acc, gJets, cells_d, xy, offset, pm, align_corners, kn, multicell, 2)
-            loss = loss_sum if loss is None else loss + loss_sum
-            pgrads = grads if pgrads is None else tuple(a + b for a, b in zip(pgrads, grads))
-        if cells.requires_grad:
-            _add_grad(cells, finish_accumulator(acc, cells_d), owned=True)
-        for prm, g in zip((W1, b1, w2, b2), pgrads):
-            if prm.requires_grad:
-                _add_grad(prm, g)
-        return loss * (loss_scale / P)
+    chunk = max(1, P if not chunk else min(chunk, P))
+    step.begin()
+    for s in range(0, P, chunk):
+        step.add(coords[s:s + chunk], loss_scale / P)
+    return step.finish()
 
 
 __all__ = ["SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
-           "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "residual_coefficients"]
+           "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "FusedPdeStep",
+           "residual_coefficients"]
