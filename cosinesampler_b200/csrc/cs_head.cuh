@@ -12,13 +12,20 @@
 //     f  = c_u u + c_u3 u^3 + sum_a (c1_a u_a + c2_a u_aa)          loss = scale * sum_p f^2
 //
 // This kernel evaluates loss AND its gradient w.r.t. the jets and the head parameters in one
-// pass: a block stages a [J*C rows] x [TP points] tile of the jets in shared memory (coalesced),
-// the 16 lanes of a half-warp are the 16 hidden units and walk groups of 4 points (weights and
-// weight-gradient accumulators live in registers; jets are read as 128-bit broadcasts), the
-// gradient w.r.t. the jets overwrites the tile and leaves coalesced.
+// pass: a block stages a [J*C rows] x [TP points] tile of the jets in shared memory (coalesced);
+// 8 lanes, two hidden units each, share a group of 4 consecutive points (weights and
+// weight-gradient accumulators live in registers; the jets are read as 128-bit broadcasts, each
+// feeding 8 FFMA); sums over the hidden units are 3-step shuffles; the gradient w.r.t. the jets
+// goes through a small shared-memory exchange, overwrites the tile and leaves coalesced.
+// Measured alternatives (profiles/README.md): one hidden unit per lane (4 FFMA per broadcast
+// LDS.128) is bound by the shared-memory pipe, 0.53 ms per 2^20 points; one thread per point with
+// the weights as constant-bank operands and the weight gradient re-partitioned through shared
+// memory is latency-bound at 12 warps per SM, 0.74 ms.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "cs_engine.cuh"
 
 namespace cs {
 
@@ -44,26 +51,35 @@ struct HeadParams {
 constexpr int HEAD_K = 16;          // hidden width (test_2d.py:44)
 constexpr int HEAD_THREADS = 128;
 constexpr int HEAD_TP = 64;         // points per tile
+#ifndef CS_HEAD_KPL
+#define CS_HEAD_KPL 2
+#endif
+#ifndef CS_HEAD_BLOCKS
+#define CS_HEAD_BLOCKS 3
+#endif
+constexpr int HEAD_KPL = CS_HEAD_KPL;   // hidden units per lane
+constexpr int HEAD_LPG = HEAD_K / HEAD_KPL;             // lanes per point group (8)
+constexpr int HEAD_GPB = HEAD_THREADS / HEAD_LPG;       // point groups per block pass (16)
 
 template <int DIM, int C> struct HeadSmem {
     static constexpr int J = 1 + 2 * DIM;
     static constexpr int ROWS = J * C;
     static constexpr int TILE_F4 = ROWS * (HEAD_TP / 4);
-    static constexpr int XCH_F4 = (HEAD_THREADS / 16) * J * HEAD_K;       // one [J][K] float4 array per half-warp
+    static constexpr int XCH_F4 = HEAD_GPB * J * HEAD_K;                 // one [J][K] float4 array per point group
+    static constexpr int W1T_F4 = C * HEAD_K / 4;                        // W1^T [C][K], read in the W1^T pass
     static constexpr int RED_F = (HEAD_THREADS / 32) * (HEAD_K * C + 2 * HEAD_K + 2);
-    static constexpr size_t BYTES = (size_t)(TILE_F4 + XCH_F4) * 16;      // the reduction scratch reuses the tile
+    static constexpr size_t BYTES = (size_t)(2 * TILE_F4 + XCH_F4 + W1T_F4) * 16;   // two tiles: the next one is prefetched
 };
 
-__device__ __forceinline__ float half_sum16(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
+// sum over the HEAD_LPG lanes that share a point group
+__device__ __forceinline__ float group_sum8(float v) {
+#pragma unroll
+    for (int o = HEAD_LPG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
 // tanh x = -em / (2 + em), em = expm1(-2|x|): accurate for small and large |x| alike, and without
-// the data-dependent branches of tanhf (which, unrolled over the 4 points of a group, made the
+// the data-dependent branches of tanhf (which, unrolled over the points of a group, made the
 // compiler spill the weight and accumulator registers)
 __device__ __forceinline__ float tanh_branchfree(float x) {
     const float em = expm1f(-2.f * fabsf(x));
@@ -71,127 +87,163 @@ __device__ __forceinline__ float tanh_branchfree(float x) {
 }
 
 template <int DIM, int C>
-__global__ void __launch_bounds__(HEAD_THREADS, (C <= 16 ? 4 : 2))
+__global__ void __launch_bounds__(HEAD_THREADS, (C <= 16 ? CS_HEAD_BLOCKS : 2))
 cs_pde_head_kernel(const HeadParams p) {
     using HS = HeadSmem<DIM, C>;
     constexpr int J = HS::J;
     constexpr int K = HEAD_K;
+    constexpr int KPL = HEAD_KPL;
     constexpr int ROWS = HS::ROWS;
     constexpr int TP = HEAD_TP;
     constexpr int TP4 = TP / 4;
-    constexpr int CPL = (C + 15) / 16;          // channels per lane in the W1^T pass
+    constexpr int CPL = (C + HEAD_LPG - 1) / HEAD_LPG;    // channels per lane in the W1^T pass
 
     extern __shared__ float4 smem4[];
-    float4* tile4 = smem4;                       // [ROWS][TP4]
-    float4* xch_all = smem4 + HS::TILE_F4;       // [8][J][K]
+    float4* tiles = smem4;                       // [2][ROWS][TP4]
+    float4* xch_all = smem4 + 2 * HS::TILE_F4;   // [GPB][J][K]
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int k = lane & 15;
-    const int hw = tid >> 4;                     // half-warp index in the block
-    float4* xch = xch_all + hw * J * K;
+    const int kq = lane & (HEAD_LPG - 1);        // this lane's hidden units: KPL*kq .. KPL*kq + KPL-1
+    const int gslot = tid / HEAD_LPG;            // point-group slot in the block
+    float4* xch = xch_all + gslot * J * K;
 
     // ---- weights in registers
-    float w1row[C];                              // W1[k][:]
+    float w1row[KPL][C];                         // W1[KPL*kq + i][:]
 #pragma unroll
-    for (int c = 0; c < C; ++c) w1row[c] = __ldg(p.W1 + k * C + c);
-    float w1col[CPL][K];                         // W1[:][c], c = k + 16 i
+    for (int i = 0; i < KPL; ++i)
 #pragma unroll
-    for (int i = 0; i < CPL; ++i)
+        for (int c = 0; c < C; ++c) w1row[i][c] = __ldg(p.W1 + (KPL * kq + i) * C + c);
+    // W1^T in shared memory for the W1^T pass (the columns would cost another C*K/8 registers)
+    float* w1t = reinterpret_cast<float*>(smem4 + 2 * HS::TILE_F4 + HS::XCH_F4);       // [C][K]
+    for (int e = tid; e < C * K; e += HEAD_THREADS) w1t[e] = __ldg(p.W1 + (e % K) * C + (e / K));
+    const float4* w1t4 = reinterpret_cast<const float4*>(w1t);
+    __syncthreads();
+    float b1k[KPL], w2k[KPL];
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) {
-            const int c = k + 16 * i;
-            w1col[i][kk] = (c < C) ? __ldg(p.W1 + kk * C + c) : 0.f;
-        }
-    const float b1k = __ldg(p.b1 + k);
-    const float w2k = __ldg(p.w2 + k);
+    for (int i = 0; i < KPL; ++i) { b1k[i] = __ldg(p.b1 + KPL * kq + i); w2k[i] = __ldg(p.w2 + KPL * kq + i); }
     const float b2 = __ldg(p.b2);
 
-    float gW1acc[C];
+    float gW1acc[KPL][C];
+    float gb1acc[KPL], gw2acc[KPL];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gW1acc[c] = 0.f;
-    float gb1acc = 0.f, gw2acc = 0.f, gb2acc = 0.f, lossacc = 0.f;
+    for (int i = 0; i < KPL; ++i) {
+        gb1acc[i] = 0.f; gw2acc[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) gW1acc[i][c] = 0.f;
+    }
+    float gb2acc = 0.f, lossacc = 0.f;
 
-    const long long ntiles = (p.P + TP - 1) / TP;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Stage rows of the [J*C, P] array, TP consecutive points each, into a tile buffer: cp.async
+    // (16 bytes, zero-filled past P) when the rows can be accessed as vectors, plain loads otherwise.
+    auto prefetch = [&](long long tile, float4* dst4) {
         const long long p0 = tile * TP;
-        // ---- stage the tile: rows of the [J*C, P] array, TP consecutive points each
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(dst4);
         for (int idx = tid; idx < ROWS * TP4; idx += HEAD_THREADS) {
             const int r = idx / TP4;
             const int v = idx - r * TP4;
             const long long pp = p0 + 4 * v;
             const float* src = p.jets + (long long)r * p.P + pp;
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.vec) {
-                if (pp < p.P) val = __ldcs(reinterpret_cast<const float4*>(src));
+                const bool ok = pp < p.P;
+                cp16z(sbase + idx * 16, ok ? src : p.jets, ok);
             } else {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pp < p.P) val.x = __ldcs(src);
                 if (pp + 1 < p.P) val.y = __ldcs(src + 1);
                 if (pp + 2 < p.P) val.z = __ldcs(src + 2);
                 if (pp + 3 < p.P) val.w = __ldcs(src + 3);
+                dst4[idx] = val;
             }
-            tile4[idx] = val;
         }
+        cp_async_commit();
+    };
+
+    const long long ntiles = (p.P + TP - 1) / TP;
+    int buf = 0;
+    if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x, tiles);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p0 = tile * TP;
+        float4* tile4 = tiles + buf * HS::TILE_F4;
+        // the next tile streams in while this one is computed
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) { prefetch(next, tiles + (buf ^ 1) * HS::TILE_F4); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
 
-        for (int grp = hw; grp < TP4; grp += HEAD_THREADS / 16) {
+        for (int grp = gslot; grp < TP4; grp += HEAD_GPB) {
             const long long gp0 = p0 + 4 * grp;
-            // ---- hidden pre-activations of 4 points for hidden unit k, all jets
-            float h[J][4];
+            // ---- A: hidden pre-activations of 4 points for this lane's hidden units, all jets
+            float h[KPL][J][4];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                h[j][0] = h[j][1] = h[j][2] = h[j][3] = 0.f;
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) h[i][j][0] = h[i][j][1] = h[i][j][2] = h[i][j][3] = 0.f;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const float4 z = tile4[(j * C + c) * TP4 + grp];
-                    h[j][0] = fmaf(w1row[c], z.x, h[j][0]);
-                    h[j][1] = fmaf(w1row[c], z.y, h[j][1]);
-                    h[j][2] = fmaf(w1row[c], z.z, h[j][2]);
-                    h[j][3] = fmaf(w1row[c], z.w, h[j][3]);
+#pragma unroll
+                    for (int i = 0; i < KPL; ++i) {
+                        h[i][j][0] = fmaf(w1row[i][c], z.x, h[i][j][0]);
+                        h[i][j][1] = fmaf(w1row[i][c], z.y, h[i][j][1]);
+                        h[i][j][2] = fmaf(w1row[i][c], z.z, h[i][j][2]);
+                        h[i][j][3] = fmaf(w1row[i][c], z.w, h[i][j][3]);
+                    }
                 }
             }
-            // ---- per point: activation derivatives, residual, and the gradient w.r.t. h
+            // ---- B: per point: activation derivatives, residual, and the gradient w.r.t. h
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float t = tanh_branchfree(h[0][i] + b1k);
-                const float s1 = 1.f - t * t;
-                const float s2 = -2.f * t * s1;
-                const float s3 = -2.f * (s1 * s1 + t * s2);
-                float u = half_sum16(w2k * t) + b2;
-                float f = p.c_u * u + p.c_u3 * u * u * u;
-                float ua[DIM], uaa[DIM];
+            for (int pt = 0; pt < 4; ++pt) {
+                float t[KPL], s1[KPL], s2[KPL];
+                float pu = 0.f, pua[DIM], puaa[DIM];
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const float hd = h[1 + a][i], hdd = h[1 + DIM + a][i];
-                    ua[a] = half_sum16(w2k * s1 * hd);
-                    uaa[a] = half_sum16(w2k * (s2 * hd * hd + s1 * hdd));
-                    f += p.c1[a] * ua[a] + p.c2[a] * uaa[a];
+                for (int a = 0; a < DIM; ++a) { pua[a] = 0.f; puaa[a] = 0.f; }
+#pragma unroll
+                for (int i = 0; i < KPL; ++i) {
+                    t[i] = tanh_branchfree(h[i][0][pt] + b1k[i]);
+                    s1[i] = 1.f - t[i] * t[i];
+                    s2[i] = -2.f * t[i] * s1[i];
+                    pu = fmaf(w2k[i], t[i], pu);
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) {
+                        const float hd = h[i][1 + a][pt], hdd = h[i][1 + DIM + a][pt];
+                        pua[a] = fmaf(w2k[i], s1[i] * hd, pua[a]);
+                        puaa[a] = fmaf(w2k[i], s2[i] * hd * hd + s1[i] * hdd, puaa[a]);
+                    }
                 }
-                const bool valid = gp0 + i < p.P;
+                const float u = group_sum8(pu) + b2;
+                float f = p.c_u * u + p.c_u3 * u * u * u;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) f += p.c1[a] * group_sum8(pua[a]) + p.c2[a] * group_sum8(puaa[a]);
+                const bool valid = gp0 + pt < p.P;
                 const float g = valid ? 2.f * p.scale * f : 0.f;
-                if (k == 0 && valid) {
+                if (kq == 0 && valid) {
                     lossacc += f * f;
-                    if (p.f_out) p.f_out[gp0 + i] = f;
+                    if (p.f_out) p.f_out[gp0 + pt] = f;
                 }
                 const float gu = g * (p.c_u + 3.f * p.c_u3 * u * u);
-                float gw2 = gu * t;
-                float gh = gu * s1;
+                if (kq == 0) gb2acc += gu;
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const float hd = h[1 + a][i], hdd = h[1 + DIM + a][i];
-                    const float g1 = g * p.c1[a], g2 = g * p.c2[a];
-                    gw2 += g1 * s1 * hd + g2 * (s2 * hd * hd + s1 * hdd);
-                    gh += g1 * s2 * hd + g2 * (s3 * hd * hd + s2 * hdd);
-                    h[1 + a][i] = w2k * (g1 * s1 + g2 * 2.f * s2 * hd);
-                    h[1 + DIM + a][i] = w2k * g2 * s1;
+                for (int i = 0; i < KPL; ++i) {
+                    const float s3 = -2.f * (s1[i] * s1[i] + t[i] * s2[i]);
+                    float gw2 = gu * t[i];
+                    float gh = gu * s1[i];
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) {
+                        const float hd = h[i][1 + a][pt], hdd = h[i][1 + DIM + a][pt];
+                        const float g1 = g * p.c1[a], g2 = g * p.c2[a];
+                        gw2 += g1 * s1[i] * hd + g2 * (s2[i] * hd * hd + s1[i] * hdd);
+                        gh += g1 * s2[i] * hd + g2 * (s3 * hd * hd + s2[i] * hdd);
+                        h[i][1 + a][pt] = w2k[i] * (g1 * s1[i] + g2 * 2.f * s2[i] * hd);
+                        h[i][1 + DIM + a][pt] = w2k[i] * g2 * s1[i];
+                    }
+                    gh *= w2k[i];
+                    h[i][0][pt] = gh;
+                    gb1acc[i] += gh;
+                    gw2acc[i] += gw2;
                 }
-                gh *= w2k;
-                h[0][i] = gh;
-                gb1acc += gh;
-                gw2acc += gw2;
-                if (k == 0) gb2acc += gu;
             }
-            // ---- weight gradient: gW1[k][c] += sum_j sum_i gH_j[k][i] * z_j[c][i]
+            // ---- D: weight gradient gW1[k][c] += sum_j sum_pt gH_j[k][pt] * z_j[c][pt]
             // (compiler barrier: re-read z from shared memory instead of keeping 4*J*C values live)
             asm volatile("" ::: "memory");
 #pragma unroll
@@ -199,29 +251,40 @@ cs_pde_head_kernel(const HeadParams p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const float4 z = tile4[(j * C + c) * TP4 + grp];
-                    gW1acc[c] = fmaf(h[j][0], z.x, gW1acc[c]);
-                    gW1acc[c] = fmaf(h[j][1], z.y, gW1acc[c]);
-                    gW1acc[c] = fmaf(h[j][2], z.z, gW1acc[c]);
-                    gW1acc[c] = fmaf(h[j][3], z.w, gW1acc[c]);
-                }
-            // ---- exchange gH over the hidden units, then gZ_j[c] = sum_k W1[k][c] gH_j[k]
 #pragma unroll
-            for (int j = 0; j < J; ++j) xch[j * K + k] = make_float4(h[j][0], h[j][1], h[j][2], h[j][3]);
+                    for (int i = 0; i < KPL; ++i) {
+                        gW1acc[i][c] = fmaf(h[i][j][0], z.x, gW1acc[i][c]);
+                        gW1acc[i][c] = fmaf(h[i][j][1], z.y, gW1acc[i][c]);
+                        gW1acc[i][c] = fmaf(h[i][j][2], z.z, gW1acc[i][c]);
+                        gW1acc[i][c] = fmaf(h[i][j][3], z.w, gW1acc[i][c]);
+                    }
+                }
+            // ---- C: exchange gH over the hidden units, then gZ_j[c] = sum_k W1[k][c] gH_j[k]
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int i = 0; i < KPL; ++i)
+                    xch[j * K + KPL * kq + i] = make_float4(h[i][j][0], h[i][j][1], h[i][j][2], h[i][j][3]);
             __syncwarp();                        // also: every lane has finished reading z of this group
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const int c = k + 16 * i;
+            for (int ci = 0; ci < CPL; ++ci) {
+                const int c = kq + HEAD_LPG * ci;
                 if (c < C) {
-#pragma unroll
+#pragma unroll 1
                     for (int j = 0; j < J; ++j) {
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int kk = 0; kk < K; ++kk) {
-                            const float4 gq = xch[j * K + kk];
-                            acc.x = fmaf(w1col[i][kk], gq.x, acc.x);
-                            acc.y = fmaf(w1col[i][kk], gq.y, acc.y);
-                            acc.z = fmaf(w1col[i][kk], gq.z, acc.z);
-                            acc.w = fmaf(w1col[i][kk], gq.w, acc.w);
+                        for (int k4 = 0; k4 < K / 4; ++k4) {
+                            const float4 wc = w1t4[c * (K / 4) + k4];           // W1[4 k4 .. 4 k4 + 3][c]
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const float4 gq = xch[j * K + 4 * k4 + kk];
+                                const float w = kk == 0 ? wc.x : kk == 1 ? wc.y : kk == 2 ? wc.z : wc.w;
+                                acc.x = fmaf(w, gq.x, acc.x);
+                                acc.y = fmaf(w, gq.y, acc.y);
+                                acc.z = fmaf(w, gq.z, acc.z);
+                                acc.w = fmaf(w, gq.w, acc.w);
+                            }
                         }
                         tile4[(j * C + c) * TP4 + grp] = acc;
                     }
@@ -247,25 +310,36 @@ cs_pde_head_kernel(const HeadParams p) {
                 if (pp + 3 < p.P) __stcs(dst + 3, val.w);
             }
         }
-        __syncthreads();
+        __syncthreads();                         // the buffer is free for the prefetch after next
+        buf ^= 1;
     }
 
-    // ---- parameter gradients and loss: halves -> warps (shared memory) -> one atomic per block
+    // ---- parameter gradients and loss: point groups of a warp (shuffles) -> warps (shared memory)
+    // -> one atomic per block and element
     float* red = reinterpret_cast<float*>(smem4);            // [4 warps][K*C + 2K + 2], reuses the tile
     constexpr int RW = K * C + 2 * K + 2;
 #pragma unroll
-    for (int c = 0; c < C; ++c) gW1acc[c] += __shfl_xor_sync(0xffffffffu, gW1acc[c], 16);
-    gb1acc += __shfl_xor_sync(0xffffffffu, gb1acc, 16);
-    gw2acc += __shfl_xor_sync(0xffffffffu, gw2acc, 16);
-    gb2acc += __shfl_xor_sync(0xffffffffu, gb2acc, 16);
-    lossacc += __shfl_xor_sync(0xffffffffu, lossacc, 16);
-    if (lane < 16) {
+    for (int o = HEAD_LPG; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) gW1acc[i][c] += __shfl_xor_sync(0xffffffffu, gW1acc[i][c], o);
+            gb1acc[i] += __shfl_xor_sync(0xffffffffu, gb1acc[i], o);
+            gw2acc[i] += __shfl_xor_sync(0xffffffffu, gw2acc[i], o);
+        }
+        gb2acc += __shfl_xor_sync(0xffffffffu, gb2acc, o);
+        lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
+    }
+    if (lane < HEAD_LPG) {
         float* rw = red + warp * RW;
 #pragma unroll
-        for (int c = 0; c < C; ++c) rw[k * C + c] = gW1acc[c];
-        rw[K * C + k] = gb1acc;
-        rw[K * C + K + k] = gw2acc;
-        if (k == 0) { rw[K * C + 2 * K] = gb2acc; rw[K * C + 2 * K + 1] = lossacc; }
+        for (int i = 0; i < KPL; ++i) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) rw[(KPL * kq + i) * C + c] = gW1acc[i][c];
+            rw[K * C + KPL * kq + i] = gb1acc[i];
+            rw[K * C + K + KPL * kq + i] = gw2acc[i];
+        }
+        if (kq == 0) { rw[K * C + 2 * K] = gb2acc; rw[K * C + 2 * K + 1] = lossacc; }
     }
     __syncthreads();
     for (int e = tid; e < RW; e += HEAD_THREADS) {
