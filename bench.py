@@ -184,7 +184,10 @@ def run_ours(args):
     stepper = dp.PointShardedStep(sampler, cells, head, residual=residual, chunk=chunk)
     from cosinesampler_b200 import jet
     fused_kw = dict(kernel=kernel, multicell=True)
-    fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=chunk, fused=fused_kw)
+    # the fused step keeps [1+2*dim, C, chunk] jets instead of [N, C, chunk] streams: 4x the chunk of
+    # the drop-in arm is the same footprint per stream
+    fchunk = 4 * chunk
+    fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
 
     def fused_resident():
         fstepper.zero_grad()
@@ -235,7 +238,7 @@ def run_ours(args):
         """The fused step from HOST buffers, same copy pipeline as step_e2e."""
         fstepper.zero_grad()
         nloc = coords_pinned.shape[0]
-        spans = [(s0, min(nloc, s0 + chunk)) for s0 in range(0, nloc, chunk)]
+        spans = [(s0, min(nloc, s0 + fchunk)) for s0 in range(0, nloc, fchunk)]
         cur = torch.cuda.current_stream()
 
         def fetch(span):
@@ -375,6 +378,7 @@ def run_ours(args):
     out["fused"] = {
         "api": "cosinesampler_b200.jet.FusedPdeStep (opt-in; SURVEY 8f ranks 1+2): jets in one gather pass, "
                "head + residual + gradients in one kernel, one scatter pass; same loss and gradients",
+        "chunk": fchunk,
         "value": total * args.steps / (ms_f * 1e-3), "unit": "points/s", "ms_per_step": ms_f / args.steps,
         "e2e": {"value": total * args.steps / (ms_f_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,

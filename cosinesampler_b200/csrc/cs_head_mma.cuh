@@ -27,17 +27,23 @@ constexpr int HM_TP = 64;               // points per tile
 constexpr int HM_TPS = HM_TP + 8;       // row stride of the tile in floats: 72 = 8 mod 32 -> conflict-free fragments
 constexpr int HM_K = 16;
 
-__device__ __forceinline__ uint32_t tf32_of(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// big = x rounded to the 10 explicit mantissa bits of TF32 (round half away from zero on the magnitude
+// bits, the same rounding as cvt.rna.tf32.f32, which ptxas expands into a 4-instruction sequence with a
+// NaN/Inf guard that finite data does not need); small = x - big exactly, handed to the tensor core as
+// it is (the hardware ignores its low 13 mantissa bits, an error below 2^-21 |x|).
 struct Tf32x2 { uint32_t big, small; };
 __device__ __forceinline__ Tf32x2 split_tf32(float x) {
     Tf32x2 r;
-    r.big = tf32_of(x);
-    r.small = tf32_of(x - __uint_as_float(r.big));
+    r.big = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    r.small = __float_as_uint(x - __uint_as_float(r.big));
     return r;
+}
+
+// tanh from one ex2.approx and one rcp.approx: absolute error a few 1e-7 (|tanh| <= 1 is the scale
+// that matters downstream: u = w2 . tanh, s1 = 1 - tanh^2).  The SIMT kernel keeps the expm1f form.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -177,7 +183,7 @@ cs_pde_head_mma_kernel(const HeadParams p) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int q = 2 * half + e;
-                    const float th = tanh_branchfree(hf[0][q] + b1g[half]);
+                    const float th = tanh_fast(hf[0][q] + b1g[half]);
                     tt[half][e] = th;
                     s1[half][e] = 1.f - th * th;
                     s2[half][e] = -2.f * th * s1[half][e];

@@ -287,83 +287,95 @@ cs_jet_fwd_kernel(const JetParams p) {
     issue(recbuf, 0, 0, allv_cur);
     cp_async_commit();
     int par = 0;
+    int n = 0;
 
+    // One loop over the work items (tile, cell): the item after (pt, n) is (pt, n+1) or, after the
+    // last cell, (next tile, 0).  A single phase-1 call site keeps the unrolled body inside the
+    // instruction cache (the first version had one per case; ncu: no_instruction stalls).
+    float acc[J][PPQ][4];
     while (pt < nptiles) {
-        float acc[J][PPQ][4];
+        if (n == 0) {
 #pragma unroll
-        for (int jt = 0; jt < J; ++jt)
+            for (int jt = 0; jt < J; ++jt)
 #pragma unroll
-            for (int t = 0; t < PPQ; ++t)
+                for (int t = 0; t < PPQ; ++t)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[jt][t][k] = 0.f;
-        const bool next_tile = ptn < nptiles;
+                    for (int k = 0; k < 4; ++k) acc[jt][t][k] = 0.f;
+        }
+        const bool last_cell = (n + 1 == ncells);
+        const int pt_nx = last_cell ? ptn : pt;
+        const int n_nx = last_cell ? 0 : n + 1;
+        const bool have_next = pt_nx < nptiles;
+        const float4* rec = recbuf + par * WS::REC1;
+        bool allv_next = true;
+#pragma unroll
+        for (int st = 0; st < NST; ++st) {
+            // ---- produce: next stage of this item, or stage 0 of the next item
+            if (st + 1 < NST) {
+                issue(rec, st + 1, n, allv_cur);
+            } else if (have_next) {
+                float gsel[PPL][DIM];
+#pragma unroll
+                for (int u = 0; u < PPL; ++u)
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) gsel[u][a] = last_cell ? gnext[u][a] : gcur[u][a];
+                allv_next = phase1(gsel, pt_nx, n_nx, par ^ 1);
+                issue(recbuf + (par ^ 1) * WS::REC1, 0, n_nx, allv_next);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();                 // everything but the group just committed has landed
 
-        for (int n = 0; n < ncells; ++n) {
-            const float4* rec = recbuf + par * WS::REC1;
-            bool allv_next = true;
+            // ---- consume stage st
+            const float4* gb = gbuf + (st & 1) * GS * 32;
 #pragma unroll
-            for (int st = 0; st < NST; ++st) {
-                // ---- produce: next stage of this cell, stage 0 of the next cell, or of the next tile
-                if (st + 1 < NST) {
-                    issue(rec, st + 1, n, allv_cur);
-                } else if (n + 1 < ncells) {
-                    allv_next = phase1(gcur, pt, n + 1, par ^ 1);
-                    issue(recbuf + (par ^ 1) * WS::REC1, 0, n + 1, allv_next);
-                } else if (next_tile) {
-                    allv_next = phase1(gnext, ptn, 0, par ^ 1);
+            for (int s = 0; s < PG; ++s) {
+                const int t = st * PG + s;
+                const int ri = PPQ * q + t;
 #pragma unroll
-                    for (int u = 0; u < PPL; ++u)
+                for (int h = 0; h < CQ; ++h) {
+                    float4 v[4];
 #pragma unroll
-                        for (int a = 0; a < DIM; ++a) gcur[u][a] = gnext[u][a];
-                    if (ptn + tstep < nptiles) load_coords(gnext, ptn + tstep);
-                    issue(recbuf + (par ^ 1) * WS::REC1, 0, 0, allv_next);
-                }
-                cp_async_commit();
-                cp_async_wait<1>();                 // everything but the group just committed has landed
-
-                // ---- consume stage st
-                const float4* gb = gbuf + (st & 1) * GS * 32;
+                    for (int cc = 0; cc < 4; ++cc) v[cc] = gb[(s * NCORN + 4 * h + cc) * 32 + lane];
 #pragma unroll
-                for (int s = 0; s < PG; ++s) {
-                    const int t = st * PG + s;
-                    const int ri = PPQ * q + t;
+                    for (int jt = 0; jt < J; ++jt) {
+                        const float4 k4 = rec[(1 + jt * CQ + h) * PTS + ri];
 #pragma unroll
-                    for (int h = 0; h < CQ; ++h) {
-                        float4 v[4];
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) v[cc] = gb[(s * NCORN + 4 * h + cc) * 32 + lane];
-#pragma unroll
-                        for (int jt = 0; jt < J; ++jt) {
-                            const float4 k4 = rec[(1 + jt * CQ + h) * PTS + ri];
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                const float cf = f4get(k4, cc);
-                                acc[jt][t][0] = fmaf(v[cc].x, cf, acc[jt][t][0]);
-                                acc[jt][t][1] = fmaf(v[cc].y, cf, acc[jt][t][1]);
-                                acc[jt][t][2] = fmaf(v[cc].z, cf, acc[jt][t][2]);
-                                acc[jt][t][3] = fmaf(v[cc].w, cf, acc[jt][t][3]);
-                            }
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const float cf = f4get(k4, cc);
+                            acc[jt][t][0] = fmaf(v[cc].x, cf, acc[jt][t][0]);
+                            acc[jt][t][1] = fmaf(v[cc].y, cf, acc[jt][t][1]);
+                            acc[jt][t][2] = fmaf(v[cc].z, cf, acc[jt][t][2]);
+                            acc[jt][t][3] = fmaf(v[cc].w, cf, acc[jt][t][3]);
                         }
                     }
                 }
             }
-            par ^= 1;
-            allv_cur = allv_next;
         }
-
-        // ---- the sums over the cells leave the registers once per tile
-        const long long qp0 = (long long)pt * PTS + PPQ * q;
+        par ^= 1;
+        allv_cur = allv_next;
+        if (last_cell) {
+            // ---- the sums over the cells leave the registers once per tile
+            const long long qp0 = (long long)pt * PTS + PPQ * q;
 #pragma unroll
-        for (int jt = 0; jt < J; ++jt)
+            for (int jt = 0; jt < J; ++jt)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float tmp[PPQ];
+                for (int k = 0; k < 4; ++k) {
+                    float tmp[PPQ];
 #pragma unroll
-                for (int t = 0; t < PPQ; ++t) tmp[t] = acc[jt][t][k];
-                row_store<PPQ>(tmp, p.jets + ((long long)jt * p.C + 4 * j + k) * p.P, qp0, p.P, svec);
-            }
-        pt = ptn;
-        ptn += tstep;
+                    for (int t = 0; t < PPQ; ++t) tmp[t] = acc[jt][t][k];
+                    row_store<PPQ>(tmp, p.jets + ((long long)jt * p.C + 4 * j + k) * p.P, qp0, p.P, svec);
+                }
+#pragma unroll
+            for (int u = 0; u < PPL; ++u)
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) gcur[u][a] = gnext[u][a];
+            pt = ptn;
+            ptn += tstep;
+            if (ptn < nptiles) load_coords(gnext, ptn);
+            n = 0;
+        } else {
+            ++n;
+        }
     }
     cp_async_wait<0>();
 }

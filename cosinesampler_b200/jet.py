@@ -241,11 +241,26 @@ def _head_params(head, C):
     return ps
 
 
+def head_buffer(C, device, dtype=torch.float32):
+    """Zeroed accumulation buffer of cs_pde_head_step: gW1 [16,C] | gb1 [16] | gw2 [16] | gb2 [1] | loss_sum [1].
+    The kernel adds into it, so one buffer can collect several chunks of points."""
+    return torch.zeros(16 * C + 34, dtype=dtype, device=device)
+
+
+def head_buffer_views(buf, C):
+    """-> (loss_sum 0-dim, (gW1 [16,C], gb1 [16], gw2 [1,16], gb2 [1])) views of a `head_buffer`."""
+    grads = (buf[:16 * C].view(16, C), buf[16 * C:16 * C + 16], buf[16 * C + 16:16 * C + 32].view(1, 16),
+             buf[16 * C + 32:16 * C + 33])
+    return buf[16 * C + 33], grads
+
+
 def pde_head_step(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=1.0, in_place=False,
-                  want_f=False):
+                  want_f=False, buf=None):
     """One launch of cs_pde_head_step on jets [1+2*dim, C, P]: returns
     (sum_p f^2 as a 0-dim tensor (unscaled), gJets, (gW1, gb1, gw2, gb2), f or None) where the
-    gradients are those of  scale * sum_p f^2.  in_place=True overwrites `jets` with gJets."""
+    gradients are those of  scale * sum_p f^2.  in_place=True overwrites `jets` with gJets.
+    buf: a `head_buffer` to accumulate into (the returned loss / gradients are then running sums
+    over every call that used it); default: a fresh one."""
     ops._check(jets, "jets")
     J, C, P = jets.shape
     if J != 1 + 2 * dim:
@@ -254,7 +269,10 @@ def pde_head_step(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=
     res = residual_coefficients(residual, dim, k2)
     gJets = jets if in_place else torch.empty_like(jets)
     # one zeroed buffer for every accumulated output: gW1 | gb1 | gw2 | gb2 | loss_sum
-    buf = torch.zeros(16 * C + 34, dtype=jets.dtype, device=jets.device)
+    if buf is None:
+        buf = head_buffer(C, jets.device, jets.dtype)
+    elif buf.numel() != 16 * C + 34 or buf.device != jets.device or buf.dtype != jets.dtype or not buf.is_contiguous():
+        raise RuntimeError("buf must come from head_buffer(C, device)")
     f = torch.empty(P, dtype=jets.dtype, device=jets.device) if want_f else None
     base = buf.data_ptr()
     nbytes = 4 * 2 * J * C * P
@@ -265,9 +283,8 @@ def pde_head_step(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=
             base + 4 * (16 * C + 16), base + 4 * (16 * C + 32), base + 4 * (16 * C + 33),
             f.data_ptr() if f is not None else None, ops._cur_stream(jets.device))
     _lib.check(rc, "cs_pde_head_step")
-    grads = (buf[:16 * C].view(16, C), buf[16 * C:16 * C + 16], buf[16 * C + 16:16 * C + 32].view(1, 16),
-             buf[16 * C + 32:16 * C + 33])
-    return buf[16 * C + 33], gJets, grads, f
+    loss_sum, grads = head_buffer_views(buf, C)
+    return loss_sum, gJets, grads, f
 
 
 class PdeHeadLoss(torch.autograd.Function):
@@ -334,24 +351,28 @@ class FusedPdeStep:
             self.offset = cell_offsets(self.cells.shape[0], self.multicell, self.cells.device)
             self.staged = ops.stage(self.cells_d)
             self.acc = new_accumulator(self.cells_d)
-        self.loss, self.pgrads, self._live = None, None, True
+            # the head kernel adds into this buffer: loss and head gradients of all chunks, no torch ops
+            self.buf = head_buffer(self.cells.shape[1], self.cells.device)
+        self.scale, self._live = None, True
 
     def add(self, xy, scale):
-        """One chunk of points xy [p, dim]; its loss contribution is scale * sum_p f^2."""
+        """One chunk of points xy [p, dim]; its loss contribution is scale * sum_p f^2 (the same
+        `scale` for every chunk of a step, e.g. loss_scale / total points)."""
         if not self._live:
             raise RuntimeError("FusedPdeStep.add before begin()")
+        if self.scale is None:
+            self.scale = float(scale)
+        elif abs(float(scale) - self.scale) > 1e-12 * abs(self.scale):
+            raise RuntimeError("FusedPdeStep.add: every chunk of a step must use the same scale")
         _check_args(self.cells_d, xy, 2)
         if xy.shape[1] != self.dim:
             raise RuntimeError("coords must be [p, %d], got %s" % (self.dim, tuple(xy.shape)))
         with torch.no_grad():
             a = (self.pm, self.align_corners, self.kn, self.multicell, 2)
             jets = jet_forward(self.cells_d, xy, self.offset, *a, staged=self.staged)
-            loss_sum, gJets, grads, _ = pde_head_step(jets, self.head, self.dim, self.residual, self.k2, scale,
-                                                      in_place=True)
+            _, gJets, _, _ = pde_head_step(jets, self.head, self.dim, self.residual, self.k2, scale,
+                                           in_place=True, buf=self.buf)
             jet_backward_into(self.acc, gJets, self.cells_d, xy, self.offset, *a)
-            part = loss_sum * scale
-            self.loss = part if self.loss is None else self.loss + part
-            self.pgrads = grads if self.pgrads is None else tuple(x + y for x, y in zip(self.pgrads, grads))
 
     def finish(self):
         if not self._live:
@@ -360,12 +381,12 @@ class FusedPdeStep:
         with torch.no_grad():
             if self.cells.requires_grad:
                 _add_grad(self.cells, finish_accumulator(self.acc, self.cells_d), owned=True)
-            if self.pgrads is not None:
-                for prm, g in zip(self.params, self.pgrads):
-                    if prm.requires_grad:
-                        _add_grad(prm, g)
-            loss = self.loss if self.loss is not None else torch.zeros((), device=self.cells.device)
-        self.acc = self.staged = self.pgrads = self.loss = None
+            loss_sum, pgrads = head_buffer_views(self.buf, self.cells.shape[1])
+            for prm, g in zip(self.params, pgrads):
+                if prm.requires_grad:
+                    _add_grad(prm, g)
+            loss = loss_sum * (self.scale if self.scale is not None else 0.0)
+        self.acc = self.staged = self.buf = None
         return loss
 
 
