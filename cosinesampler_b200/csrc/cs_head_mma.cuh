@@ -15,8 +15,8 @@
 // only C needs an exchange through shared memory.
 //
 // Precision: fp32 parity is kept with the error-compensated 3xTF32 scheme -- every operand x is
-// split into big = tf32(x) and small = tf32(x - big) and a product is accumulated as
-// small*big + big*small + big*big in fp32 -- which carries 22 mantissa bits per operand.
+// split into big = tf32(x) and small = x - big and a product is accumulated as
+// small*big + big*small + big*big in fp32 -- which carries 21-22 mantissa bits per operand.
 #pragma once
 #include "cs_head.cuh"
 
