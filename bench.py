@@ -45,8 +45,10 @@ CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tenso
 
 def ncu_traffic_bytes(label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a stage kernel, from the committed
-    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg{3,4}_summary.json)."""
-    for name in ("ncu_stages_cfg3_summary.json", "ncu_stages_cfg4_summary.json"):
+    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg{3,4}_summary.json; the
+    fused kernels: ncu_fused_cfg{3,4}_summary.json, captured at 2^20 / 2^22 points per launch)."""
+    for name in ("ncu_stages_cfg3_summary.json", "ncu_stages_cfg4_summary.json",
+                 "ncu_fused_cfg3_summary.json", "ncu_fused_cfg4_summary.json"):
         try:
             with open(os.path.join(ROOT, "profiles", "r1", name)) as f:
                 kernels = json.load(f)["kernels"]
@@ -394,6 +396,9 @@ def run_ours(args):
             "achieved": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9, 1),
             "frac": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9 / peak, 4),
             "bytes_per_launch": fstage[ftop]["bytes_per_launch"], "ms_avg": round(fstage[ftop]["ms_avg"], 4),
+            "traffic": None if ncu_traffic_bytes(ftop) is None else int(
+                ncu_traffic_bytes(ftop) * (min(fchunk, coords_host.shape[0]) / float(2 ** 20 if dim == 2 else 2 ** 22))),
+            "traffic_note": "ncu dram bytes of the committed capture, scaled from its points per launch to this run's",
             "share_of_step": round(fstage[ftop]["ms_total"] / ms_f, 4)},
         "chain_roofline": {"note": "the reference formulation's minimal bytes per step (BASELINE.md section 3) "
                                    "over the fused step's time", "achieved": round(fchain_gbs, 1),
