@@ -46,7 +46,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -118,8 +118,12 @@ cs_pde_head_mma_kernel(const HeadParams p) {
     const float b2 = __ldg(p.b2);
 
     float accW[NBD][4];                         // gW1 fragments: rows k = g, g+8; columns c = 8 nb + 2t, 2t+1
+    float accWs[NBD][4];                        // the small (correction) terms: a second accumulator chain
 #pragma unroll
-    for (int nb = 0; nb < NBD; ++nb) accW[nb][0] = accW[nb][1] = accW[nb][2] = accW[nb][3] = 0.f;
+    for (int nb = 0; nb < NBD; ++nb) {
+        accW[nb][0] = accW[nb][1] = accW[nb][2] = accW[nb][3] = 0.f;
+        accWs[nb][0] = accWs[nb][1] = accWs[nb][2] = accWs[nb][3] = 0.f;
+    }
     float gb1acc[2] = {0.f, 0.f}, gw2acc[2] = {0.f, 0.f};
     float gb2acc = 0.f, lossacc = 0.f;
 
@@ -162,14 +166,23 @@ cs_pde_head_mma_kernel(const HeadParams p) {
             // ---- A: H_j = W1 Z_j.  B fragment: Z_j[c = 8s + t (+4)][p = g]
             float hf[J][4];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                hf[j][0] = hf[j][1] = hf[j][2] = hf[j][3] = 0.f;
+            for (int j = 0; j < J; ++j) hf[j][0] = hf[j][1] = hf[j][2] = hf[j][3] = 0.f;
+            // the J accumulator chains are independent: issue the three 3xTF32 terms jet by jet so that
+            // consecutive MMAs never wait for each other
 #pragma unroll
-                for (int s = 0; s < KSA; ++s) {
-                    const Tf32x2 b0 = split_tf32(tl[(j * C + 8 * s + t) * TPS + pb + g]);
-                    const Tf32x2 b1 = split_tf32(tl[(j * C + 8 * s + t + 4) * TPS + pb + g]);
-                    mma_3xtf32(hf[j], wab[s], was[s], b0, b1);
+            for (int s = 0; s < KSA; ++s) {
+                Tf32x2 b0[J], b1[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    b0[j] = split_tf32(tl[(j * C + 8 * s + t) * TPS + pb + g]);
+                    b1[j] = split_tf32(tl[(j * C + 8 * s + t + 4) * TPS + pb + g]);
                 }
+#pragma unroll
+                for (int j = 0; j < J; ++j) mma_tf32(hf[j], was[s], b0[j].big, b1[j].big);
+#pragma unroll
+                for (int j = 0; j < J; ++j) mma_tf32(hf[j], wab[s], b0[j].small, b1[j].small);
+#pragma unroll
+                for (int j = 0; j < J; ++j) mma_tf32(hf[j], wab[s], b0[j].big, b1[j].big);
             }
             // hf[j][2*half + e] = H_j[k = g + 8 half][p = 2t + e]
             // ---- B: per point (e = 0, 1): sums over the 16 hidden units = this lane's two + the 8 groups
@@ -252,11 +265,19 @@ cs_pde_head_mma_kernel(const HeadParams p) {
                 const float av[4] = {hf[j][0], hf[j][2], hf[j][1], hf[j][3]};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const Tf32x2 sp = split_tf32(av[e]); ab[e] = sp.big; as[e] = sp.small; }
+                Tf32x2 z0[NBD], z1[NBD];
 #pragma unroll
                 for (int nb = 0; nb < NBD; ++nb) {
                     const float2 z = *reinterpret_cast<const float2*>(tl + (j * C + 8 * nb + g) * TPS + pb + 2 * t);
-                    mma_3xtf32(accW[nb], ab, as, split_tf32(z.x), split_tf32(z.y));
+                    z0[nb] = split_tf32(z.x);
+                    z1[nb] = split_tf32(z.y);
                 }
+#pragma unroll
+                for (int nb = 0; nb < NBD; ++nb) mma_tf32(accWs[nb], as, z0[nb].big, z1[nb].big);
+#pragma unroll
+                for (int nb = 0; nb < NBD; ++nb) mma_tf32(accW[nb], ab, z0[nb].big, z1[nb].big);
+#pragma unroll
+                for (int nb = 0; nb < NBD; ++nb) mma_tf32(accWs[nb], ab, z0[nb].small, z1[nb].small);
             }
             // ---- C: gZ_j = W1^T gH_j.  gH goes through shared memory: [j*16 + k][8 points]
 #pragma unroll
@@ -266,23 +287,32 @@ cs_pde_head_mma_kernel(const HeadParams p) {
             }
             __syncwarp();                        // also: every lane has finished reading z of this point block
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                Tf32x2 b0[2], b1[2];
+            for (int mb = 0; mb < MBC; ++mb) {
+                float d[J][4];
+#pragma unroll
+                for (int j = 0; j < J; ++j) d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    b0[ks] = split_tf32(xch[(j * K + 8 * ks + t) * 8 + g]);
-                    b1[ks] = split_tf32(xch[(j * K + 8 * ks + t + 4) * 8 + g]);
+                    Tf32x2 b0[J], b1[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        b0[j] = split_tf32(xch[(j * K + 8 * ks + t) * 8 + g]);
+                        b1[j] = split_tf32(xch[(j * K + 8 * ks + t + 4) * 8 + g]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < J; ++j) mma_tf32(d[j], wcs[mb][ks], b0[j].big, b1[j].big);
+#pragma unroll
+                    for (int j = 0; j < J; ++j) mma_tf32(d[j], wcb[mb][ks], b0[j].small, b1[j].small);
+#pragma unroll
+                    for (int j = 0; j < J; ++j) mma_tf32(d[j], wcb[mb][ks], b0[j].big, b1[j].big);
                 }
+                // d[j][2*half + e] = gZ_j[c = 16mb + g + 8 half][p = 2t + e]: overwrites z in the tile
 #pragma unroll
-                for (int mb = 0; mb < MBC; ++mb) {
-                    float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) mma_3xtf32(d, wcb[mb][ks], wcs[mb][ks], b0[ks], b1[ks]);
-                    // d[2*half + e] = gZ_j[c = 16mb + g + 8 half][p = 2t + e]: overwrites z in the tile
+                for (int j = 0; j < J; ++j) {
                     if (16 * mb + g < C)
-                        *reinterpret_cast<float2*>(tl + (j * C + 16 * mb + g) * TPS + pb + 2 * t) = make_float2(d[0], d[1]);
+                        *reinterpret_cast<float2*>(tl + (j * C + 16 * mb + g) * TPS + pb + 2 * t) = make_float2(d[j][0], d[j][1]);
                     if (16 * mb + g + 8 < C)
-                        *reinterpret_cast<float2*>(tl + (j * C + 16 * mb + g + 8) * TPS + pb + 2 * t) = make_float2(d[2], d[3]);
+                        *reinterpret_cast<float2*>(tl + (j * C + 16 * mb + g + 8) * TPS + pb + 2 * t) = make_float2(d[j][2], d[j][3]);
                 }
             }
             __syncwarp();                        // xch is reused by the next point block
@@ -331,10 +361,10 @@ cs_pde_head_mma_kernel(const HeadParams p) {
         float* rw = red + warp * RW;
 #pragma unroll
         for (int nb = 0; nb < NBD; ++nb) {
-            rw[g * C + 8 * nb + 2 * t] = accW[nb][0];
-            rw[g * C + 8 * nb + 2 * t + 1] = accW[nb][1];
-            rw[(g + 8) * C + 8 * nb + 2 * t] = accW[nb][2];
-            rw[(g + 8) * C + 8 * nb + 2 * t + 1] = accW[nb][3];
+            rw[g * C + 8 * nb + 2 * t] = accW[nb][0] + accWs[nb][0];
+            rw[g * C + 8 * nb + 2 * t + 1] = accW[nb][1] + accWs[nb][1];
+            rw[(g + 8) * C + 8 * nb + 2 * t] = accW[nb][2] + accWs[nb][2];
+            rw[(g + 8) * C + 8 * nb + 2 * t + 1] = accW[nb][3] + accWs[nb][3];
         }
         if (t == 0) {
             rw[K * C + g] = gb1acc[0]; rw[K * C + g + 8] = gb1acc[1];
