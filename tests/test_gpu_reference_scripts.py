@@ -73,3 +73,46 @@ def test_reference_script_quantities_and_assertion(cuda, dim):
     assert strict >= 0.999
     assert ok_ours >= ok_ref - 2e-3
     assert worst_ours <= 2.0 * worst_ref + 1e-6 * np.abs(z).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_scripts_through_the_fused_step(cuda, dim):
+    """The same scripts' shapes ([96,4,16,16] / [50,4,16,16,16], 100 000 points, C = 4: one lane per
+    point quad in the jet kernels, the SIMT head) through `jet.fused_pde_step`: loss and d loss / d cells
+    against the fp32 sampler chain on the GPU (the scripts' comparison) and the fp64 chain on the CPU."""
+    from cosinesampler_b200 import jet
+    from cosinesampler_b200.chain import make_head as _mk  # noqa: F401  (same head as oracle.make_head)
+    _, b, t = _run(dim, cuda)
+    if dim == 2:
+        np.random.seed(51)
+        torch.manual_seed(51)
+        cells0 = torch.rand([96, 4, 16, 16])
+        yx = np.random.rand(100000, 2)
+        yx[..., 1] = yx[..., 1] * 2 - 1
+        pts = torch.tensor(yx).float()
+        coords0 = torch.stack([pts[:, 0] * 2 - 1, pts[:, 1]], -1)
+        residual = "t2d"
+    else:
+        torch.manual_seed(6)
+        cells0 = torch.rand([50, 4, 16, 16, 16])
+        np.random.seed(6)
+        pts = torch.tensor(np.random.rand(100000, 3)).float()
+        coords0 = torch.stack([pts[:, 2], pts[:, 0], pts[:, 1]], -1)
+        residual = "laplace"
+    head = make_head(4, seed=3).to(cuda)
+    cells = cells0.to(cuda).requires_grad_(True)
+    loss = jet.fused_pde_step(cells, coords0.to(cuda).contiguous(), head, residual, kernel="cosine", chunk=30000)
+    assert_close_scaled(loss, t["loss"], "fused loss vs fp64 chain", rtol=1e-4)
+    assert_close_scaled(loss, b["loss"], "fused loss vs fp32 sampler chain", rtol=1e-4)
+    x = cells.grad.reshape(-1).double().cpu().numpy()
+    y = b["dloss"].reshape(-1).detach().double().cpu().numpy()
+    z = t["dloss"].reshape(-1).detach().numpy()
+    big = np.abs(z) > 1e-3 * np.abs(z).max()
+    ok_ours = (np.abs(x - z) <= 1e-4 * np.abs(z))[big].mean()
+    ok_ref = (np.abs(y - z) <= 1e-4 * np.abs(z))[big].mean()
+    worst_ours = np.abs(x - z)[big].max()
+    worst_ref = np.abs(y - z)[big].max()
+    print("fused test_%dd.py dloss: within rtol=1e-4 of fp64: fused %.5f, fp32 sampler %.5f; worst |err| vs fp64: "
+          "fused %.3e, fp32 sampler %.3e" % (dim, ok_ours, ok_ref, worst_ours, worst_ref))
+    assert ok_ours >= ok_ref - 2e-3
+    assert worst_ours <= 2.0 * worst_ref + 1e-6 * np.abs(z).max()
