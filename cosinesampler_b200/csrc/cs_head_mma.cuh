@@ -50,14 +50,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// d += a * b, error-compensated: small terms first
-__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4],
-                                           Tf32x2 b0, Tf32x2 b1) {
-    mma_tf32(d, as, b0.big, b1.big);
-    mma_tf32(d, ab, b0.small, b1.small);
-    mma_tf32(d, ab, b0.big, b1.big);
-}
-
 template <int DIM, int C> struct HeadMmaSmem {
     static constexpr int J = 1 + 2 * DIM;
     static constexpr int ROWS = J * C;

@@ -161,7 +161,10 @@ template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
     static constexpr int NST = PPQ / PG;
     static constexpr int GSLOTS = PG * NCORN;
     static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer (float4)
-    static constexpr int GBUF = 2 * GSLOTS * 32;                 // gather ring, double-buffered by stage
+    // ring depth: 2D keeps two stages in flight behind the one consumed (0.217 -> 0.207 ms per 2^20 points);
+    // in 3D the third slot costs a resident warp per SM and loses (2.29 -> 2.72 ms per 2^22 points)
+    static constexpr int RING = (DIM == 2) ? 3 : 2;
+    static constexpr int GBUF = RING * GSLOTS * 32;              // gather ring
     static constexpr int TOTAL_FWD = 2 * REC1 + GBUF;
     static constexpr int TOTAL_BWD = REC1;
 };
@@ -200,7 +203,7 @@ cs_jet_fwd_kernel(const JetParams p) {
     const int q = lane >> LSHIFT;
     const int j = lane & (L - 1);
     float4* recbuf = smem4 + (size_t)warp * WS::TOTAL_FWD;   // [2][F4][PTS]
-    float4* gbuf = recbuf + 2 * WS::REC1;                    // [2][GS][32]
+    float4* gbuf = recbuf + 2 * WS::REC1;                    // [RING][GS][32]
     const unsigned gdst = (unsigned)__cvta_generic_to_shared(gbuf + lane);
 
     const bool svec = p.svec != 0;
@@ -259,9 +262,9 @@ cs_jet_fwd_kernel(const JetParams p) {
         }
         return __all_sync(0xffffffffu, allv);       // also a warp barrier: records are visible
     };
-    auto issue = [&](const float4* rec, int st, int n, bool allv) {
+    auto issue = [&](const float4* rec, int st, int slot, int n, bool allv) {
         const char* vsrc = vlane + (long long)n * cellb;
-        const unsigned d0 = gdst + (st & 1) * GS * 512;
+        const unsigned d0 = gdst + slot * GS * 512;
 #pragma unroll
         for (int s = 0; s < PG; ++s) {
             const float4 hd = rec[PPQ * q + st * PG + s];
@@ -278,20 +281,27 @@ cs_jet_fwd_kernel(const JetParams p) {
             }
         }
     };
+    static_assert(NST == 2, "the ring schedule below assumes two stages per work item");
 
-    // ---- prologue
+    // ---- prologue: records of the first item, both of its stages in flight
     load_coords(gcur, pt);
     bool allv_cur = phase1(gcur, pt, 0, 0);
     int ptn = pt + tstep;
     if (ptn < nptiles) load_coords(gnext, ptn);
-    issue(recbuf, 0, 0, allv_cur);
+    issue(recbuf, 0, 0, 0, allv_cur);
     cp_async_commit();
+    if (WS::RING == 3) {
+        issue(recbuf, 1, 1, 0, allv_cur);
+        cp_async_commit();
+    }
     int par = 0;
     int n = 0;
+    int slot0 = 0;                              // ring slot of stage 0 of the current item
 
     // One loop over the work items (tile, cell): the item after (pt, n) is (pt, n+1) or, after the
-    // last cell, (next tile, 0).  A single phase-1 call site keeps the unrolled body inside the
-    // instruction cache (the first version had one per case; ncu: no_instruction stalls).
+    // last cell, (next tile, 0).  While stage st of an item is consumed, stage st of the NEXT item is
+    // issued, so two stages (2 x PG points x 2^DIM corners x 16 B per lane) are always in flight:
+    // the kernel is bound by bytes in flight over L2 latency (one stage ahead: 5.0 TB/s of gathers).
     float acc[J][PPQ][4];
     while (pt < nptiles) {
         if (n == 0) {
@@ -307,26 +317,39 @@ cs_jet_fwd_kernel(const JetParams p) {
         const int n_nx = last_cell ? 0 : n + 1;
         const bool have_next = pt_nx < nptiles;
         const float4* rec = recbuf + par * WS::REC1;
+        const float4* rec_nx = recbuf + (par ^ 1) * WS::REC1;
         bool allv_next = true;
+        if (have_next) {
+            float gsel[PPL][DIM];
+#pragma unroll
+            for (int u = 0; u < PPL; ++u)
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) gsel[u][a] = last_cell ? gnext[u][a] : gcur[u][a];
+            allv_next = phase1(gsel, pt_nx, n_nx, par ^ 1);
+        }
 #pragma unroll
         for (int st = 0; st < NST; ++st) {
-            // ---- produce: next stage of this item, or stage 0 of the next item
-            if (st + 1 < NST) {
-                issue(rec, st + 1, n, allv_cur);
-            } else if (have_next) {
-                float gsel[PPL][DIM];
-#pragma unroll
-                for (int u = 0; u < PPL; ++u)
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) gsel[u][a] = last_cell ? gnext[u][a] : gcur[u][a];
-                allv_next = phase1(gsel, pt_nx, n_nx, par ^ 1);
-                issue(recbuf + (par ^ 1) * WS::REC1, 0, n_nx, allv_next);
+            int slot_c;
+            if (WS::RING == 3) {
+                // ---- produce: the same stage of the next item, two ring slots ahead
+                slot_c = slot0 + st;
+                if (slot_c >= 3) slot_c -= 3;
+                int slot_p = slot_c + 2;
+                if (slot_p >= 3) slot_p -= 3;
+                if (have_next) issue(rec_nx, st, slot_p, n_nx, allv_next);
+                cp_async_commit();
+                cp_async_wait<2>();             // everything but the two groups just committed has landed
+            } else {
+                // ---- produce: the next stage of this item, or stage 0 of the next item
+                slot_c = st;
+                if (st + 1 < NST) issue(rec, st + 1, st + 1, n, allv_cur);
+                else if (have_next) issue(rec_nx, 0, 0, n_nx, allv_next);
+                cp_async_commit();
+                cp_async_wait<1>();             // everything but the group just committed has landed
             }
-            cp_async_commit();
-            cp_async_wait<1>();                 // everything but the group just committed has landed
 
             // ---- consume stage st
-            const float4* gb = gbuf + (st & 1) * GS * 32;
+            const float4* gb = gbuf + slot_c * GS * 32;
 #pragma unroll
             for (int s = 0; s < PG; ++s) {
                 const int t = st * PG + s;
@@ -351,6 +374,8 @@ cs_jet_fwd_kernel(const JetParams p) {
                 }
             }
         }
+        slot0 += NST;
+        if (slot0 >= WS::RING) slot0 -= WS::RING;
         par ^= 1;
         allv_cur = allv_next;
         if (last_cell) {
