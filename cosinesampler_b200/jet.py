@@ -390,10 +390,47 @@ class FusedPdeStep:
         return loss
 
 
+def head_is_fusable(head, C):
+    """True when `head` is the Linear(C,16)-Tanh-Linear(16,1) stack cs_pde_head_step implements."""
+    try:
+        _head_params(head, C)
+        return True
+    except NotImplementedError:
+        return False
+
+
+def jet_autograd_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
+                      align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0):
+    """The same step for any Linear/Tanh head: jets from `SamplerJet2d/3d` (one gather pass, one
+    scatter pass), the head's chain rule and the residual in torch (`jet_mlp`), first-order autograd."""
+    from .chain import _residual
+    if isinstance(residual, dict):
+        raise NotImplementedError("a residual given as coefficients needs the fused head; pass a name")
+    dim = coords.shape[1]
+    S = SamplerJet2d if dim == 2 else SamplerJet3d
+    P = coords.shape[0]
+    chunk = max(1, P if not chunk else min(chunk, P))
+    params = [cells] + [q for q in head.parameters() if q.requires_grad]
+    total = None
+    for s in range(0, P, chunk):
+        xy = coords[s:s + chunk]
+        jets = S.apply(cells, xy, padding_mode, align_corners, kernel, multicell)
+        u, first, second = jet_mlp(head, jets, dim)
+        loss = torch.sum(_residual(u, first, second, residual, k2) ** 2) * (loss_scale / P)
+        loss.backward(inputs=params)
+        total = loss.detach() if total is None else total + loss.detach()
+    return total if total is not None else torch.zeros((), device=cells.device)
+
+
 def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
                    align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0):
     """`FusedPdeStep` over coords [P, dim] in chunks of `chunk` points: accumulates `cells.grad` and the
-    head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor."""
+    head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor.  Heads other than
+    Linear(C,16)-Tanh-Linear(16,1) take `jet_autograd_step` (jet kernels + torch head) instead."""
+    ops._check(cells, "input")
+    if cells.dim() in (4, 5) and not head_is_fusable(head, cells.shape[1]):
+        return jet_autograd_step(cells, coords, head, residual, k2, padding_mode, align_corners, kernel,
+                                 multicell, chunk, loss_scale)
     step = FusedPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell)
     P = coords.shape[0]
     chunk = max(1, P if not chunk else min(chunk, P))
@@ -404,5 +441,6 @@ def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, p
 
 
 __all__ = ["SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
-           "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "FusedPdeStep",
+           "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "FusedPdeStep", "jet_autograd_step",
+           "head_is_fusable",
            "residual_coefficients"]

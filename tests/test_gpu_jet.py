@@ -288,3 +288,35 @@ def test_fused_head_rejects_other_heads(cuda):
     # jet_mlp (torch ops) takes any Linear/Tanh stack
     u, first, second = jet.jet_mlp(wide, jets, 2)
     assert u.shape == (64, 1) and len(first) == 2 and len(second) == 2
+
+
+def test_fused_pde_step_falls_back_for_other_heads(cuda):
+    """A wider / deeper Linear-Tanh head takes the jet kernels + torch head path and still equals the
+    drop-in chain."""
+    from cosinesampler_b200 import jet
+    from cosinesampler_b200.chain import training_step
+    from cosine_sampler_2d import CosineSampler2d
+    gen = torch.Generator().manual_seed(21)
+    P, C = 4096, 8
+    cells0 = torch.rand(3, C, 32, 32, generator=gen)
+    cols = [(torch.rand(P, 1, generator=gen) * 2 - 1).to(cuda) for _ in range(2)]
+
+    def make():
+        torch.manual_seed(4)
+        return torch.nn.Sequential(torch.nn.Linear(C, 24), torch.nn.Tanh(), torch.nn.Linear(24, 12), torch.nn.Tanh(),
+                                   torch.nn.Linear(12, 1)).to(cuda)
+    res = {}
+    for mode in ("dropin", "fused"):
+        cells = torch.nn.Parameter(cells0.clone().to(cuda))
+        head = make()
+        assert not jet.head_is_fusable(head, C)
+        if mode == "dropin":
+            loss = training_step(lambda c, g: CosineSampler2d.apply(c, g, "zeros", True, "cosine", True), cells, cols,
+                                 head, "helmholtz")
+        else:
+            loss = jet.fused_pde_step(cells, torch.cat(cols, -1).contiguous(), head, "helmholtz", chunk=1500)
+        res[mode] = (loss.detach(), cells.grad, [p.grad for p in head.parameters()])
+    assert_close_scaled(res["fused"][0], res["dropin"][0], "fallback loss", rtol=1e-4)
+    assert_close_scaled(res["fused"][1], res["dropin"][1], "fallback cells.grad", rtol=1e-4, atol_scale=2e-5)
+    for a, b in zip(res["fused"][2], res["dropin"][2]):
+        assert_close_scaled(a, b, "fallback head grad", rtol=1e-4, atol_scale=2e-5)
