@@ -189,7 +189,20 @@ def run_ours(args):
     # the fused step keeps [1+2*dim, C, chunk] jets instead of [N, C, chunk] streams: 4x the chunk of
     # the drop-in arm is the same footprint per stream
     fchunk = 4 * chunk
-    fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
+    reduce_kind = "none (single GPU)"
+    fstepper = None
+    if world > 1 and not args.nccl_reduce:
+        try:        # gradient reduce fused with the layout change over NVLink peer memory (peer.py)
+            fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw,
+                                           peer_reduce=True)
+            reduce_kind = "peer-memory kernel cs_peer_allreduce_from_channel_last (symmetric memory over NVLink)"
+        except Exception as exc:          # no symmetric memory on this box: NCCL
+            print("peer-memory reduce unavailable (%s); using NCCL" % exc, file=sys.stderr)
+            fstepper = None
+    if fstepper is None:
+        fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
+        if world > 1:
+            reduce_kind = "NCCL all-reduce of one flat bucket"
 
     def fused_resident():
         fstepper.zero_grad()
@@ -251,7 +264,7 @@ def run_ours(args):
             return t, ev
 
         fs = jet.FusedPdeStep(cells, head, residual, kernel=kernel, multicell=True)
-        fs.begin()
+        fs.begin(fstepper.reducer)
         nxt = fetch(spans[0])
         for i, span in enumerate(spans):
             t, ev = nxt
@@ -261,7 +274,8 @@ def run_ours(args):
             t.record_stream(cur)
             fs.add(t, 1.0 / float(total))
         loss = fs.finish()
-        dp.allreduce_grads(fstepper.params())
+        if fstepper.reducer is None:
+            dp.allreduce_grads(fstepper.params())
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         cur.synchronize()
         return loss_host
@@ -319,7 +333,7 @@ def run_ours(args):
     flaunches = _lib.launch_count() - n0
     ops.profiler = None
     floss_t = fused_resident().detach().clone()
-    if world > 1:
+    if world > 1 and not fstepper.loss_is_global:
         dist.all_reduce(floss_t)
     floss_val = float(floss_t.item())
     for _ in range(max(1, min(args.warmup, 2))):
@@ -380,7 +394,7 @@ def run_ours(args):
     out["fused"] = {
         "api": "cosinesampler_b200.jet.FusedPdeStep (opt-in; SURVEY 8f ranks 1+2): jets in one gather pass, "
                "head + residual + gradients in one kernel, one scatter pass; same loss and gradients",
-        "chunk": fchunk,
+        "chunk": fchunk, "gradient_reduce": reduce_kind,
         "value": total * args.steps / (ms_f * 1e-3), "unit": "points/s", "ms_per_step": ms_f / args.steps,
         "e2e": {"value": total * args.steps / (ms_f_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
@@ -514,6 +528,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2 ** 19,
                     help="points per CPU-baseline step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-reduce", action="store_true",
+                    help="fused arm: reduce the gradients with NCCL instead of the peer-memory kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,7 @@ EXPORTS = (
     "cs_version", "cs_last_error", "cs_launch_count",
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
-    "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step",
+    "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step", "cs_peer_allreduce_from_channel_last",
 )
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
@@ -86,6 +86,8 @@ def load():
     lib.cs_pde_head_step.restype = ctypes.c_int
     lib.cs_pde_head_step.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, ctypes.POINTER(PdeResidual),
                                      ctypes.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cs_peer_allreduce_from_channel_last.restype = ctypes.c_int
+    lib.cs_peer_allreduce_from_channel_last.argtypes = [i32, i32, vp, vp, i32, i32, i64, vp, vp, i32, vp]
     lib.cs_to_channel_last.restype = ctypes.c_int
     lib.cs_to_channel_last.argtypes = [vp, vp, i32, i32, i64, vp]
     lib.cs_from_channel_last.restype = ctypes.c_int

@@ -244,6 +244,70 @@ int launch_reforder(const cs_problem* pb, const cs::StageParams& p, void* stream
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Gradient all-reduce over peer memory, fused with the layout change.
+// Every rank holds a channel-last accumulator [N, T, C] in symmetric memory (mapped into all peers
+// over NVLink / NVSwitch).  The (32 texel x 32 channel) tiles are dealt round-robin to the ranks;
+// the owner of a tile loads it from every peer's accumulator, sums in rank order, transposes through
+// shared memory and stores the channel-first result into every peer's output [N, C, T]: a
+// reduce-scatter and an all-gather in one kernel, each byte crossing NVLink once per direction, and
+// the cs_from_channel_last pass for free.  One extra block sums a small vector (head gradients, loss)
+// from all peers for this rank.  The caller brackets the launch with symmetric-memory barriers.
+// ---------------------------------------------------------------------------
+struct PeerParams {
+    const float* acc[CS_MAX_PEERS];
+    float* out[CS_MAX_PEERS];
+    const float* small_in[CS_MAX_PEERS];
+    float* small_out;
+    int world, rank, N, C, small_n, tiles_y;
+    long long T, tiles_x, total_tiles, my_tiles;
+};
+
+__device__ __forceinline__ float ld_peer(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) cs_peer_reduce_kernel(const PeerParams p) {
+    __shared__ float tile[32][33];          // [channel][texel]
+    const long long b = blockIdx.x;
+    if (b < p.my_tiles) {
+        const long long id = b * p.world + p.rank;
+        const long long bx = id % p.tiles_x;
+        const long long rem = id / p.tiles_x;
+        const int by = (int)(rem % p.tiles_y);
+        const int n = (int)(rem / p.tiles_y);
+        const long long t0 = bx * 32;
+        const int c0 = by * 32;
+        const int ct = min(32, p.C - c0);
+        for (int idx = threadIdx.x; idx < 32 * ct; idx += 256) {
+            const int t = idx / ct, c = idx - t * ct;
+            if (t0 + t < p.T) {
+                const long long off = ((long long)n * p.T + t0 + t) * p.C + c0 + c;
+                float s = 0.f;
+                for (int r = 0; r < p.world; ++r) s += ld_peer(p.acc[r] + off);
+                tile[c][t] = s;
+            }
+        }
+        __syncthreads();
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        for (int c = ty; c < ct; c += 8) {
+            if (t0 + tx < p.T) {
+                const float v = tile[c][tx];
+                const long long off = ((long long)n * p.C + c0 + c) * p.T + t0 + tx;
+                for (int r = 0; r < p.world; ++r) p.out[r][off] = v;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < p.small_n; i += 256) {
+            float s = 0.f;
+            for (int r = 0; r < p.world; ++r) s += ld_peer(p.small_in[r] + i);
+            p.small_out[i] = s;
+        }
+    }
+}
+
 int layout_launch(const float* src, float* dst, int N, int C, long long T, int mode, void* stream) {
     if (N < 0 || C < 0 || T < 0) return fail(CS_EINVAL, "negative size");
     if (N == 0 || C == 0 || T == 0) return 0;
@@ -413,6 +477,40 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float* jets, const
     p.vec = (P % 4 == 0) && aligned16(jets) && aligned16(gJets);
     cudaError_t e = cs::launch_head_any(dim, C, p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "pde head kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int cs_peer_allreduce_from_channel_last(int32_t world, int32_t rank, const float* const* acc_ptrs,
+                                        float* const* out_ptrs, int32_t N, int32_t C, int64_t T,
+                                        const float* const* small_ptrs, float* small_out, int32_t small_n,
+                                        void* stream) {
+    if (world < 1 || world > CS_MAX_PEERS) return fail(CS_EUNSUPPORTED, "world must be 1..%d, got %d", CS_MAX_PEERS, world);
+    if (rank < 0 || rank >= world) return fail(CS_EINVAL, "bad rank %d of %d", rank, world);
+    if (N < 0 || C < 0 || T < 0 || small_n < 0) return fail(CS_EINVAL, "negative size");
+    if (!acc_ptrs || !out_ptrs) return fail(CS_EINVAL, "NULL pointer table");
+    if (small_n > 0 && (!small_ptrs || !small_out)) return fail(CS_EINVAL, "small vector given without pointers");
+    PeerParams p;
+    memset(&p, 0, sizeof(p));
+    for (int r = 0; r < world; ++r) {
+        if (!acc_ptrs[r] || !out_ptrs[r]) return fail(CS_EINVAL, "NULL peer buffer for rank %d", r);
+        p.acc[r] = acc_ptrs[r]; p.out[r] = out_ptrs[r];
+        if (small_n > 0) {
+            if (!small_ptrs[r]) return fail(CS_EINVAL, "NULL small buffer for rank %d", r);
+            p.small_in[r] = small_ptrs[r];
+        }
+    }
+    p.small_out = small_out; p.small_n = small_n;
+    p.world = world; p.rank = rank; p.N = N; p.C = C; p.T = T;
+    p.tiles_x = (T + 31) / 32; p.tiles_y = (C + 31) / 32;
+    p.total_tiles = (long long)N * p.tiles_y * p.tiles_x;
+    p.my_tiles = p.total_tiles > rank ? (p.total_tiles - rank + world - 1) / world : 0;
+    const long long blocks = p.my_tiles + (small_n > 0 ? 1 : 0);
+    if (blocks < 1) return 0;
+    if (blocks > 0x7fffffffll) return fail(CS_EUNSUPPORTED, "peer reduce grid too large");
+    cs_peer_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "peer reduce launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }

@@ -47,13 +47,25 @@ class PointShardedStep:
     gradients.  loss_scale = shard/total makes the summed gradient the gradient of the
     mean over *all* points."""
 
-    def __init__(self, sampler, cells, head, residual="helmholtz", chunk=None, group=None, fused=None):
+    def __init__(self, sampler, cells, head, residual="helmholtz", chunk=None, group=None, fused=None,
+                 peer_reduce=False):
         """fused: None = `sampler` is a drop-in operator driven through `chain.training_step`
         (nested autograd, the reference's call pattern); a dict of `jet.fused_pde_step` keyword
-        arguments (kernel=..., multicell=...) = the fused jet path (`sampler` is ignored)."""
+        arguments (kernel=..., multicell=...) = the fused jet path (`sampler` is ignored).
+        peer_reduce (fused path only): sum the gradients over the ranks with the fused peer-memory
+        kernel (`peer.PeerReducer`, NVLink symmetric memory) instead of NCCL; the loss returned by
+        `step` is then the loss over ALL ranks' points (`loss_is_global`)."""
         self.sampler, self.cells, self.head = sampler, cells, head
         self.residual, self.chunk, self.group = residual, chunk, group
         self.fused = fused
+        self.reducer = None
+        self.loss_is_global = False
+        if peer_reduce and fused is not None and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size(group) > 1:
+            from .jet import head_buffer_size
+            from .peer import PeerReducer
+            self.reducer = PeerReducer(cells, head_buffer_size(cells.shape[1]), group)
+            self.loss_is_global = True
 
     def params(self):
         return [self.cells] + list(self.head.parameters())
@@ -67,8 +79,10 @@ class PointShardedStep:
             from .jet import fused_pde_step
             xy = local_coords if torch.is_tensor(local_coords) else torch.cat(list(local_coords), -1)
             loss = fused_pde_step(self.cells, xy.contiguous(), self.head, self.residual, chunk=self.chunk,
-                                  loss_scale=xy.shape[0] / float(total_points), **self.fused)
-            allreduce_grads(self.params(), self.group)
+                                  loss_scale=xy.shape[0] / float(total_points), reducer=self.reducer,
+                                  **self.fused)
+            if self.reducer is None:
+                allreduce_grads(self.params(), self.group)
             return loss
         from .chain import training_step
         local = local_coords[0].shape[0]

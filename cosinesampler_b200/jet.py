@@ -241,6 +241,10 @@ def _head_params(head, C):
     return ps
 
 
+def head_buffer_size(C):
+    return 16 * C + 34
+
+
 def head_buffer(C, device, dtype=torch.float32):
     """Zeroed accumulation buffer of cs_pde_head_step: gW1 [16,C] | gb1 [16] | gw2 [16] | gb2 [1] | loss_sum [1].
     The kernel adds into it, so one buffer can collect several chunks of points."""
@@ -271,7 +275,7 @@ def pde_head_step(jets, head, dim, residual="helmholtz", k2=math.pi ** 2, scale=
     # one zeroed buffer for every accumulated output: gW1 | gb1 | gw2 | gb2 | loss_sum
     if buf is None:
         buf = head_buffer(C, jets.device, jets.dtype)
-    elif buf.numel() != 16 * C + 34 or buf.device != jets.device or buf.dtype != jets.dtype or not buf.is_contiguous():
+    elif buf.numel() != head_buffer_size(C) or buf.device != jets.device or buf.dtype != jets.dtype or not buf.is_contiguous():
         raise RuntimeError("buf must come from head_buffer(C, device)")
     f = torch.empty(P, dtype=jets.dtype, device=jets.device) if want_f else None
     base = buf.data_ptr()
@@ -345,14 +349,21 @@ class FusedPdeStep:
         self.params = _head_params(head, cells.shape[1])
         self._live = False
 
-    def begin(self):
+    def begin(self, reducer=None):
+        """reducer: a `peer.PeerReducer` whose symmetric-memory accumulators receive the scatters, so
+        that `finish` can sum over the ranks with one kernel over NVLink instead of NCCL."""
         with torch.no_grad():
             self.cells_d = self.cells.detach()
             self.offset = cell_offsets(self.cells.shape[0], self.multicell, self.cells.device)
             self.staged = ops.stage(self.cells_d)
-            self.acc = new_accumulator(self.cells_d)
-            # the head kernel adds into this buffer: loss and head gradients of all chunks, no torch ops
-            self.buf = head_buffer(self.cells.shape[1], self.cells.device)
+            self.reducer = reducer
+            if reducer is not None:
+                self.acc = reducer.accumulator()
+                self.buf = reducer.small_buffer()
+            else:
+                self.acc = new_accumulator(self.cells_d)
+                # the head kernel adds into this buffer: loss and head gradients of all chunks, no torch ops
+                self.buf = head_buffer(self.cells.shape[1], self.cells.device)
         self.scale, self._live = None, True
 
     def add(self, xy, scale):
@@ -379,14 +390,22 @@ class FusedPdeStep:
             raise RuntimeError("FusedPdeStep.finish before begin()")
         self._live = False
         with torch.no_grad():
-            if self.cells.requires_grad:
-                _add_grad(self.cells, finish_accumulator(self.acc, self.cells_d), owned=True)
-            loss_sum, pgrads = head_buffer_views(self.buf, self.cells.shape[1])
+            if self.reducer is not None:
+                # sum over the ranks + layout change in one kernel over peer memory; the loss and the
+                # head gradients returned are those of ALL ranks
+                gcells, buf = self.reducer.reduce()
+                if self.cells.requires_grad:
+                    _add_grad(self.cells, gcells)
+            else:
+                buf = self.buf
+                if self.cells.requires_grad:
+                    _add_grad(self.cells, finish_accumulator(self.acc, self.cells_d), owned=True)
+            loss_sum, pgrads = head_buffer_views(buf, self.cells.shape[1])
             for prm, g in zip(self.params, pgrads):
                 if prm.requires_grad:
                     _add_grad(prm, g)
             loss = loss_sum * (self.scale if self.scale is not None else 0.0)
-        self.acc = self.staged = self.buf = None
+        self.acc = self.staged = self.buf = self.reducer = None
         return loss
 
 
@@ -423,18 +442,20 @@ def jet_autograd_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2
 
 
 def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
-                   align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0):
+                   align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0, reducer=None):
     """`FusedPdeStep` over coords [P, dim] in chunks of `chunk` points: accumulates `cells.grad` and the
     head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor.  Heads other than
     Linear(C,16)-Tanh-Linear(16,1) take `jet_autograd_step` (jet kernels + torch head) instead."""
     ops._check(cells, "input")
     if cells.dim() in (4, 5) and not head_is_fusable(head, cells.shape[1]):
+        if reducer is not None:
+            raise NotImplementedError("the peer-memory reduce needs the fused head")
         return jet_autograd_step(cells, coords, head, residual, k2, padding_mode, align_corners, kernel,
                                  multicell, chunk, loss_scale)
     step = FusedPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell)
     P = coords.shape[0]
     chunk = max(1, P if not chunk else min(chunk, P))
-    step.begin()
+    step.begin(reducer)
     for s in range(0, P, chunk):
         step.add(coords[s:s + chunk], loss_scale / P)
     return step.finish()

@@ -1,0 +1,79 @@
+"""Gradient all-reduce over peer memory, fused with the layout change.
+
+The fused step scatters `d loss / d cells` into a channel-last accumulator and has to (a) sum it over
+the ranks and (b) transpose it back to the reference layout.  With NCCL that is a transpose, a flat
+copy, a 16 MiB ring all-reduce (~0.2 ms on 8 B200s, latency-bound) and a copy back.  Here the
+accumulator lives in symmetric memory (torch.distributed._symmetric_memory: allocations mapped into
+every peer over NVLink / NVSwitch) and one kernel, `cs_peer_allreduce_from_channel_last`, does
+reduce-scatter + all-gather + transpose: each rank owns every world-th tile, sums it over all peers'
+accumulators, and stores the channel-first result into all peers' outputs.  The head's gradients
+and the loss ride along as a small vector.  torch is used for the symmetric allocations and the two
+barriers that bracket the kernel; the data movement is ours.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+MAX_PEERS = 8
+
+
+class PeerReducer:
+    """Symmetric buffers + the fused reduce for one `cells` shape and one process group."""
+
+    def __init__(self, cells, n_small, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not dist.is_initialized():
+            raise RuntimeError("PeerReducer needs an initialised process group")
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        if self.world > MAX_PEERS:
+            raise RuntimeError("PeerReducer supports at most %d ranks, got %d" % (MAX_PEERS, self.world))
+        ops._check(cells, "input")
+        self.shape = tuple(cells.shape)
+        self.N, self.C = cells.shape[:2]
+        self.T = cells[0, 0].numel()
+        self.n_small = int(n_small)
+        dev = cells.device
+        n = self.N * self.T * self.C
+        self.acc = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.out = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.small = symm_mem.empty(max(self.n_small, 4), dtype=torch.float32, device=dev)
+        self.h_acc = symm_mem.rendezvous(self.acc, group)
+        self.h_out = symm_mem.rendezvous(self.out, group)
+        self.h_small = symm_mem.rendezvous(self.small, group)
+        self.rank = self.h_acc.rank
+        self.small_out = torch.zeros(max(self.n_small, 4), dtype=torch.float32, device=dev)
+        arr = ctypes.c_void_p * MAX_PEERS
+        self._acc_ptrs = arr(*[int(x) for x in self.h_acc.buffer_ptrs])
+        self._out_ptrs = arr(*[int(x) for x in self.h_out.buffer_ptrs])
+        self._small_ptrs = arr(*[int(x) for x in self.h_small.buffer_ptrs])
+        self.acc.zero_()
+        self.small.zero_()
+        # nobody may start scattering into / reading from a peer before everyone has zeroed
+        self.h_acc.barrier(channel=0)
+
+    def accumulator(self):
+        """The zeroed channel-last accumulator [N, T, C] of this step (zeroed after the previous reduce)."""
+        return self.acc.view(self.N, self.T, self.C)
+
+    def small_buffer(self):
+        """The zeroed small vector (head gradients | loss) of this step."""
+        return self.small[:self.n_small]
+
+    def reduce(self):
+        """-> (sum over ranks of the accumulators as [N,C,*S] (a view of the symmetric output buffer,
+        valid until the next reduce), sum over ranks of the small vectors).  Stream-ordered; no host sync."""
+        dev = self.acc.device
+        self.h_acc.barrier(channel=0)                 # every rank has finished scattering
+        with ops._on_device(dev):
+            rc = _lib.load().cs_peer_allreduce_from_channel_last(
+                self.world, self.rank, self._acc_ptrs, self._out_ptrs, self.N, self.C, self.T,
+                self._small_ptrs, self.small_out.data_ptr(), self.n_small, ops._cur_stream(dev))
+        _lib.check(rc, "cs_peer_allreduce_from_channel_last")
+        self.h_acc.barrier(channel=1)                 # every rank has finished reading / writing peers
+        self.acc.zero_()                              # ready for the next step
+        self.small.zero_()
+        return self.out.view(self.shape), self.small_out[:self.n_small]

@@ -161,6 +161,20 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float *jets, const
                      float *gJets, float *gW1, float *gb1, float *gw2, float *gb2, float *loss_sum,
                      float *f_out, void *stream);
 
+/* ---- Gradient all-reduce over peer memory, fused with the layout change ------------
+ * acc_ptrs[r] / out_ptrs[r] (r < world <= CS_MAX_PEERS): device addresses, valid on THIS device, of rank r's
+ * channel-last accumulator [N, T, C] and channel-first output [N, C, T] (symmetric memory: NVLink-mapped
+ * peer allocations).  Tiles are dealt round-robin to the ranks; the owner sums a tile over all peers in rank
+ * order, transposes it and stores it into every peer's output, so after a barrier every rank holds the same
+ * bits: sum_r acc_r in the reference layout.  small_ptrs[r] (nullable when small_n == 0): a vector of small_n
+ * floats per rank, summed over the ranks into this rank's small_out.  The caller must order the launch
+ * between two cross-rank barriers (all scatters done before; nobody reuses the buffers until after). */
+#define CS_MAX_PEERS 8
+int cs_peer_allreduce_from_channel_last(int32_t world, int32_t rank, const float *const *acc_ptrs,
+                                        float *const *out_ptrs, int32_t N, int32_t C, int64_t T,
+                                        const float *const *small_ptrs, float *small_out, int32_t small_n,
+                                        void *stream);
+
 /* Staging between the reference layout and the channel-last layout.
  * src [N, C, T] -> dst [N, T, C]   (T = D*H*W) */
 int cs_to_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T, void *stream);
