@@ -199,6 +199,11 @@ def run_ours(args):
         except Exception as exc:          # no symmetric memory on this box: NCCL
             print("peer-memory reduce unavailable (%s); using NCCL" % exc, file=sys.stderr)
             fstepper = None
+        # all ranks must take the same path: one vote, NCCL unless every rank has its reducer
+        vote = torch.tensor([1.0 if fstepper is not None else 0.0], device=device)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if float(vote.item()) < 0.5:
+            fstepper = None
     if fstepper is None:
         fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
         if world > 1:
