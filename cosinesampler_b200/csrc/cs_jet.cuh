@@ -157,7 +157,7 @@ template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
     using JL = JetLayout<DIM, ORDER>;
     static constexpr int NCORN = 1 << DIM;
     static constexpr int PTS = PPQ * (32 >> LSHIFT);            // points per warp tile
-    static constexpr int PG = (DIM == 2 && PPQ >= 2) ? 2 : 1;    // points per pipeline stage
+    static constexpr int PG = (PPQ >= 2) ? PPQ / 2 : 1;           // points per pipeline stage (two stages per item)
     static constexpr int NST = PPQ / PG;
     static constexpr int GSLOTS = PG * NCORN;
     static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer (float4)
@@ -561,7 +561,10 @@ cudaError_t launch_jet_one(const JetParams& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int DIM> struct JetPPQ { static constexpr int value = (DIM == 2) ? 4 : 2; };
+#ifndef CS_JET_PPQ2D
+#define CS_JET_PPQ2D 4
+#endif
+template <int DIM> struct JetPPQ { static constexpr int value = (DIM == 2) ? CS_JET_PPQ2D : 2; };
 
 template <int DIM, int LSHIFT>
 cudaError_t launch_jet_variant(int order, bool backward, JetParams& p, cudaStream_t s) {
