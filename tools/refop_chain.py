@@ -118,6 +118,15 @@ def main():
                 p.grad = None
             return chain.training_step(sampler, cells, [coords[:, a:a + 1] for a in range(dim)], head,
                                        residual=residual)
+        from cosinesampler_b200 import jet
+
+        def step_fused():
+            cells.grad = None
+            for p in head.parameters():
+                p.grad = None
+            return jet.fused_pde_step(cells, coords, head, residual, kernel=kname)
+        l_fused = float(step_fused()); g_fused = cells.grad.clone()
+        t_fused = time_step(step_fused, warm=3, iters=10)
         l_ours = float(step(ours)); g_ours = cells.grad.clone()
         l_ref = float(step(theirs)); g_ref = cells.grad.clone()
         rel = float((g_ours - g_ref).abs().max() / g_ref.abs().max())
@@ -125,8 +134,11 @@ def main():
         t_ref = time_step(lambda: step(theirs))
         print(json.dumps({"config": name, "points": P, "ms_step_ours": round(t_ours, 3),
                           "ms_step_reference_cuda_op": round(t_ref, 3), "speedup": round(t_ref / t_ours, 2),
-                          "loss_ours": l_ours, "loss_reference_op": l_ref,
-                          "max_abs_diff_cells_grad_over_max": rel}), flush=True)
+                          "ms_step_fused": round(t_fused, 3), "speedup_fused_vs_reference_cuda_op": round(t_ref / t_fused, 1),
+                          "loss_ours": l_ours, "loss_reference_op": l_ref, "loss_fused": l_fused,
+                          "max_abs_diff_cells_grad_over_max": rel,
+                          "max_abs_diff_cells_grad_fused_vs_reference_op_over_max":
+                              float((g_fused - g_ref).abs().max() / g_ref.abs().max())}), flush=True)
 
 
 if __name__ == "__main__":
