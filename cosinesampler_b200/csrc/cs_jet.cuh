@@ -119,6 +119,63 @@ __device__ __forceinline__ void build_jet_record(float4* rec4, int i, const floa
                 make_float4(coef[k][4 * h], coef[k][4 * h + 1], coef[k][4 * h + 2], coef[k][4 * h + 3]);
 }
 
+// Forward-pass record: the jets are separable in the axes, so the gather pass only needs the
+// per-axis kernel values (w0, w1, m k', m^2 k'') -- 1 + DIM float4 per (cell, point) instead of
+// 1 + J * 2^DIM / 4 -- and contracts the corners axis by axis (slab_contract below):
+//   field 0 = (base texel, corner-valid mask), field 1 + a = (w0, w1, d, e) of axis a.
+// Corners that are out of bounds are zero-filled by the gather, which is what skipping them means.
+template <int DIM, int ORDER, int PTS>
+__device__ __forceinline__ void build_jet_axis_record(float4* rec4, int i, const float (&g)[DIM], bool in_range,
+                                                      float off, const JetParams& p) {
+    int base = 0, mask = 0;
+    float4 ax[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) ax[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_range) {
+        bool ok = true;
+        bool lo_ok[DIM], hi_ok[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            const AxisRec ar = axis_setup(g[a], p.size[a], off, p, p.align != 0, ORDER);
+            ok = ok && ar.ok;
+            base += ar.l * p.tstride[a];
+            lo_ok[a] = (ar.l >= 0) && (ar.l < p.size[a]);
+            hi_ok[a] = (ar.l + 1 >= 0) && (ar.l + 1 < p.size[a]);
+            ax[a] = make_float4(ar.w0, ar.w1, ar.d, (ORDER >= 2) ? ar.e : 0.f);
+        }
+        if (ok) {
+#pragma unroll
+            for (int c = 0; c < (1 << DIM); ++c) {
+                bool valid = true;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) valid = valid && (((c >> a) & 1) ? hi_ok[a] : lo_ok[a]);
+                if (valid) mask |= 1 << c;
+            }
+        }
+    }
+    rec4[i] = make_float4(__int_as_float(base), __int_as_float(mask), 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) rec4[(1 + a) * PTS + i] = ax[a];
+}
+
+// One channel of one (x, y) slab of corners: v00 = (x low, y low), v10 = (x high, y low), v01, v11;
+// ax, ay = (w0, w1, d, e) of the two axes.  dW = (-d, +d), d2W = (+e, -e).
+struct SlabJet { float A, X, XX, Y, YY; };
+__device__ __forceinline__ SlabJet slab_contract(float v00, float v10, float v01, float v11, const float4& ax,
+                                                 const float4& ay) {
+    const float a0 = fmaf(v10, ax.y, v00 * ax.x);
+    const float a1 = fmaf(v11, ax.y, v01 * ax.x);
+    const float d0 = v10 - v00, d1 = v11 - v01;
+    SlabJet s;
+    s.A = fmaf(a1, ay.y, a0 * ay.x);
+    s.X = ax.z * fmaf(d1, ay.y, d0 * ay.x);
+    s.XX = -ax.w * fmaf(d1, ay.y, d0 * ay.x);
+    const float da = a1 - a0;
+    s.Y = da * ay.z;
+    s.YY = -da * ay.w;
+    return s;
+}
+
 // PPQ consecutive points of one row of a [rows, P] array
 template <int PPQ>
 __device__ __forceinline__ void row_store(const float (&v)[PPQ], float* row, long long p0, long long P, bool vec) {
@@ -153,6 +210,9 @@ __device__ __forceinline__ void row_load(float (&v)[PPQ], const float* row, long
     }
 }
 
+#ifndef CS_JET_RING3D
+#define CS_JET_RING3D 3
+#endif
 template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
     using JL = JetLayout<DIM, ORDER>;
     static constexpr int NCORN = 1 << DIM;
@@ -160,12 +220,13 @@ template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
     static constexpr int PG = (PPQ >= 2) ? PPQ / 2 : 1;           // points per pipeline stage (two stages per item)
     static constexpr int NST = PPQ / PG;
     static constexpr int GSLOTS = PG * NCORN;
-    static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer (float4)
+    static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer of the backward pass (float4)
+    static constexpr int REC1F = (1 + DIM) * PTS;                // one record buffer of the forward pass (per-axis values)
     // ring depth: 2D keeps two stages in flight behind the one consumed (0.217 -> 0.207 ms per 2^20 points);
     // in 3D the third slot costs a resident warp per SM and loses (2.29 -> 2.72 ms per 2^22 points)
-    static constexpr int RING = (DIM == 2) ? 3 : 2;
+    static constexpr int RING = (DIM == 2) ? 3 : CS_JET_RING3D;
     static constexpr int GBUF = RING * GSLOTS * 32;              // gather ring
-    static constexpr int TOTAL_FWD = 2 * REC1 + GBUF;
+    static constexpr int TOTAL_FWD = 2 * REC1F + GBUF;
     static constexpr int TOTAL_BWD = REC1;
 };
 
@@ -185,9 +246,7 @@ cs_jet_fwd_kernel(const JetParams p) {
     using JL = JetLayout<DIM, ORDER>;
     using WS = JetSmem<DIM, LSHIFT, ORDER, PPQ>;
     constexpr int NCORN = JL::NCORN;
-    constexpr int CQ = JL::CQ;
     constexpr int J = JL::J;
-    constexpr int F4 = JL::FIELDS4;
     constexpr int L = 1 << LSHIFT;
     constexpr int PTS = WS::PTS;
     constexpr int PPL = (PTS + 31) / 32;
@@ -203,7 +262,7 @@ cs_jet_fwd_kernel(const JetParams p) {
     const int q = lane >> LSHIFT;
     const int j = lane & (L - 1);
     float4* recbuf = smem4 + (size_t)warp * WS::TOTAL_FWD;   // [2][F4][PTS]
-    float4* gbuf = recbuf + 2 * WS::REC1;                    // [RING][GS][32]
+    float4* gbuf = recbuf + 2 * WS::REC1F;                    // [RING][GS][32]
     const unsigned gdst = (unsigned)__cvta_generic_to_shared(gbuf + lane);
 
     const bool svec = p.svec != 0;
@@ -249,14 +308,14 @@ cs_jet_fwd_kernel(const JetParams p) {
     auto phase1 = [&](const float (&g)[PPL][DIM], int tile, int n, int par) -> bool {
         const long long pt0 = (long long)tile * PTS;
         const float off = __ldg(p.offset + n);
-        float4* rb = recbuf + par * WS::REC1;
+        float4* rb = recbuf + par * WS::REC1F;
         __syncwarp();                               // everyone is done reading this record buffer
         bool allv = true;
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
             const int i = u * 32 + lane;
             if (i < PTS) {
-                build_jet_record<DIM, ORDER, PTS>(rb, i, g[u], pt0 + i < p.P, off, p);
+                build_jet_axis_record<DIM, ORDER, PTS>(rb, i, g[u], pt0 + i < p.P, off, p);
                 allv = allv && (__float_as_int(rb[i].y) == FULL);
             }
         }
@@ -316,8 +375,8 @@ cs_jet_fwd_kernel(const JetParams p) {
         const int pt_nx = last_cell ? ptn : pt;
         const int n_nx = last_cell ? 0 : n + 1;
         const bool have_next = pt_nx < nptiles;
-        const float4* rec = recbuf + par * WS::REC1;
-        const float4* rec_nx = recbuf + (par ^ 1) * WS::REC1;
+        const float4* rec = recbuf + par * WS::REC1F;
+        const float4* rec_nx = recbuf + (par ^ 1) * WS::REC1F;
         bool allv_next = true;
         if (have_next) {
             float gsel[PPL][DIM];
@@ -348,27 +407,46 @@ cs_jet_fwd_kernel(const JetParams p) {
                 cp_async_wait<1>();             // everything but the group just committed has landed
             }
 
-            // ---- consume stage st
+            // ---- consume stage st: corners contracted axis by axis with the per-axis kernel values
             const float4* gb = gbuf + slot_c * GS * 32;
 #pragma unroll
             for (int s = 0; s < PG; ++s) {
                 const int t = st * PG + s;
                 const int ri = PPQ * q + t;
-#pragma unroll
-                for (int h = 0; h < CQ; ++h) {
+                const float4 ax = rec[1 * PTS + ri];
+                const float4 ay = rec[2 * PTS + ri];
+                if (DIM == 2) {
                     float4 v[4];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) v[cc] = gb[(s * NCORN + 4 * h + cc) * 32 + lane];
+                    for (int cc = 0; cc < 4; ++cc) v[cc] = gb[(s * NCORN + cc) * 32 + lane];
 #pragma unroll
-                    for (int jt = 0; jt < J; ++jt) {
-                        const float4 k4 = rec[(1 + jt * CQ + h) * PTS + ri];
+                    for (int k = 0; k < 4; ++k) {
+                        const SlabJet sj = slab_contract(f4get(v[0], k), f4get(v[1], k), f4get(v[2], k), f4get(v[3], k), ax, ay);
+                        acc[0][t][k] += sj.A;
+                        acc[1][t][k] += sj.X;
+                        acc[2][t][k] += sj.Y;
+                        if (ORDER >= 2) { acc[3][t][k] += sj.XX; acc[4][t][k] += sj.YY; }
+                    }
+                } else {
+                    const float4 az = rec[(DIM == 3 ? 3 : 2) * PTS + ri];
+                    float4 v0[4], v1[4];
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const float cf = f4get(k4, cc);
-                            acc[jt][t][0] = fmaf(v[cc].x, cf, acc[jt][t][0]);
-                            acc[jt][t][1] = fmaf(v[cc].y, cf, acc[jt][t][1]);
-                            acc[jt][t][2] = fmaf(v[cc].z, cf, acc[jt][t][2]);
-                            acc[jt][t][3] = fmaf(v[cc].w, cf, acc[jt][t][3]);
+                    for (int cc = 0; cc < 4; ++cc) {
+                        v0[cc] = gb[(s * NCORN + cc) * 32 + lane];
+                        v1[cc] = gb[(s * NCORN + 4 + cc) * 32 + lane];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const SlabJet lo = slab_contract(f4get(v0[0], k), f4get(v0[1], k), f4get(v0[2], k), f4get(v0[3], k), ax, ay);
+                        const SlabJet hi = slab_contract(f4get(v1[0], k), f4get(v1[1], k), f4get(v1[2], k), f4get(v1[3], k), ax, ay);
+                        acc[0][t][k] += fmaf(hi.A, az.y, lo.A * az.x);
+                        acc[1][t][k] += fmaf(hi.X, az.y, lo.X * az.x);
+                        acc[2][t][k] += fmaf(hi.Y, az.y, lo.Y * az.x);
+                        acc[DIM][t][k] += (hi.A - lo.A) * az.z;
+                        if (ORDER >= 2) {
+                            acc[1 + DIM][t][k] += fmaf(hi.XX, az.y, lo.XX * az.x);
+                            acc[2 + DIM][t][k] += fmaf(hi.YY, az.y, lo.YY * az.x);
+                            acc[2 * DIM][t][k] += (lo.A - hi.A) * az.w;
                         }
                     }
                 }
