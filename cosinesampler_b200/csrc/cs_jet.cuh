@@ -21,8 +21,10 @@
 // points, L = C/4 lanes share a quad of PPQ points, each lane holds 4 channels (one 16-byte
 // gather per corner, one red.global.add.v4.f32 per corner); the warp walks the N cells of
 // its tile and keeps the sums over the cells in registers.  Phase 1 (one point per lane)
-// writes the finished per-corner coefficients of all J jets to a shared-memory record; the
-// corner gathers run through a per-warp cp.async ring one stage ahead of their use.
+// writes a shared-memory record per (cell, point): the per-axis kernel values in the forward
+// pass (the jets are separable in the axes, so the corners are contracted axis by axis), the
+// finished per-corner coefficients of all J jets in the backward pass (one red per corner);
+// the corner gathers run through a per-warp cp.async ring two stages ahead of their use.
 #pragma once
 #include "cs_engine.cuh"
 
@@ -222,8 +224,8 @@ template <int DIM, int LSHIFT, int ORDER, int PPQ> struct JetSmem {
     static constexpr int GSLOTS = PG * NCORN;
     static constexpr int REC1 = JL::FIELDS4 * PTS;               // one record buffer of the backward pass (float4)
     static constexpr int REC1F = (1 + DIM) * PTS;                // one record buffer of the forward pass (per-axis values)
-    // ring depth: 2D keeps two stages in flight behind the one consumed (0.217 -> 0.207 ms per 2^20 points);
-    // in 3D the third slot costs a resident warp per SM and loses (2.29 -> 2.72 ms per 2^22 points)
+    // ring depth: two stages in flight behind the one consumed (2D 0.217 -> 0.207 ms per 2^20 points; in 3D it
+    // only pays with the small per-axis records, which leave room for it at full occupancy)
     static constexpr int RING = (DIM == 2) ? 3 : CS_JET_RING3D;
     static constexpr int GBUF = RING * GSLOTS * 32;              // gather ring
     static constexpr int TOTAL_FWD = 2 * REC1F + GBUF;
