@@ -1,3 +1,6 @@
+#!/bin/bash
+# Short GPU pass on the final tree (run under gpurun): parity tests, smoke, both bench workloads and the
+# ncu --set full captures of the three fused kernels (exported to CSV; the reports are deleted).
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --maxfail 25 --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"
