@@ -73,3 +73,47 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert rc == -1 and b"NULL" in lib.cs_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "cs_forward")
+
+
+def _prototypes():
+    """name -> number of parameters, parsed from the header."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|uint64_t|const char \*)\s*(cs_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_ctypes_signatures_have_the_arity_of_the_header():
+    """every binding in _lib.py passes exactly as many arguments as the C prototype takes"""
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    protos = _prototypes()
+    assert set(protos) == set(_lib.EXPORTS)
+    for name, n in protos.items():
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None and len(argtypes) == n, (name, n, argtypes)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    pb = _lib.Problem()
+    pb.dim, pb.N, pb.C, pb.D, pb.H, pb.W, pb.P = 2, 1, 6, 1, 8, 8, 16
+    pb.field_layout = _lib.LAYOUT_CHANNEL_LAST
+    assert lib.cs_jet_forward(ctypes.byref(pb), 2, None, None, None, None, None) == -2
+    assert b"C in" in lib.cs_last_error()
+    pb.C = 8
+    assert lib.cs_jet_forward(ctypes.byref(pb), 3, None, None, None, None, None) == -1
+    assert b"order" in lib.cs_last_error()
+    pb.field_layout = _lib.LAYOUT_CHANNEL_FIRST
+    assert lib.cs_jet_backward(ctypes.byref(pb), 2, None, None, None, None, None) == -2
+    res = _lib.PdeResidual()
+    assert lib.cs_pde_head_step(2, 6, 16, None, None, None, None, None, ctypes.byref(res), 1.0,
+                                None, None, None, None, None, None, None, None) == -2
+    assert lib.cs_pde_head_step(2, 8, 16, None, None, None, None, None, ctypes.byref(res), 1.0,
+                                None, None, None, None, None, None, None, None) == -1
+    assert lib.cs_peer_allreduce_from_channel_last(9, 0, None, None, 1, 8, 64, None, None, 0, None) == -2
+    assert lib.cs_peer_allreduce_from_channel_last(2, 0, None, None, 1, 8, 64, None, None, 0, None) == -1
