@@ -15,6 +15,7 @@ EXPORTS = (
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
     "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step", "cs_peer_allreduce_from_channel_last",
+    "cs_bin_workspace_bytes", "cs_bin_points", "cs_head_premix", "cs_head_postmix", "cs_pde_fused_step",
 )
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
@@ -88,6 +89,17 @@ def load():
                                      ctypes.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cs_peer_allreduce_from_channel_last.restype = ctypes.c_int
     lib.cs_peer_allreduce_from_channel_last.argtypes = [i32, i32, vp, vp, i32, i32, i64, vp, vp, i32, vp]
+    lib.cs_bin_workspace_bytes.restype = ctypes.c_int
+    lib.cs_bin_workspace_bytes.argtypes = [pp, ctypes.POINTER(ctypes.c_int64)]
+    lib.cs_bin_points.restype = ctypes.c_int
+    lib.cs_bin_points.argtypes = [pp, vp, vp, vp, vp, vp, i64, vp]
+    lib.cs_head_premix.restype = ctypes.c_int
+    lib.cs_head_premix.argtypes = [i32, i32, i64, i32, vp, vp, vp, vp]
+    lib.cs_head_postmix.restype = ctypes.c_int
+    lib.cs_head_postmix.argtypes = [i32, i32, i64, i32, vp, i32, vp, vp, vp, i32, vp, vp]
+    lib.cs_pde_fused_step.restype = ctypes.c_int
+    lib.cs_pde_fused_step.argtypes = [pp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(PdeResidual), ctypes.c_float,
+                                      vp, vp, vp, vp, vp, i32, vp]
     lib.cs_to_channel_last.restype = ctypes.c_int
     lib.cs_to_channel_last.argtypes = [vp, vp, i32, i32, i64, vp]
     lib.cs_from_channel_last.restype = ctypes.c_int

@@ -40,6 +40,8 @@ import torch
 
 from . import _lib, ops
 
+_lib.load()  # the operators have no CPU / PyTorch fallback: importing them without the library raises
+
 
 def padding_mode_enum(padding_mode):
     """mod2d:4-10: anything that is not 'zeros' or 'border' means reflection."""

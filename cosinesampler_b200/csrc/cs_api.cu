@@ -11,6 +11,7 @@
 #include "cs_engine.cuh"
 #include "cs_jet.cuh"
 #include "cs_head.cuh"
+#include "cs_fused.cuh"
 
 namespace cs {
 // one function per (dim, field vector width, log2 lanes) variant, each in its own object file
@@ -24,6 +25,10 @@ CS_DECLJ(launch_jet_d2_l0) CS_DECLJ(launch_jet_d2_l1) CS_DECLJ(launch_jet_d2_l2)
 CS_DECLJ(launch_jet_d3_l0) CS_DECLJ(launch_jet_d3_l1) CS_DECLJ(launch_jet_d3_l2) CS_DECLJ(launch_jet_d3_l3)
 #undef CS_DECLJ
 cudaError_t launch_head_any(int dim, int C, const HeadParams& p, cudaStream_t s);
+#define CS_DECLF(name) cudaError_t name(bool aggregate, FusedParams& p, cudaStream_t s);
+CS_DECLF(launch_fused_d2_l0) CS_DECLF(launch_fused_d2_l1) CS_DECLF(launch_fused_d2_l2) CS_DECLF(launch_fused_d2_l3)
+CS_DECLF(launch_fused_d3_l0) CS_DECLF(launch_fused_d3_l1) CS_DECLF(launch_fused_d3_l2) CS_DECLF(launch_fused_d3_l3)
+#undef CS_DECLF
 }  // namespace cs
 
 namespace {
@@ -376,6 +381,62 @@ int jet_run(const cs_problem* pb, int order, bool backward, const float* field_i
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused step (cs_fused.cuh): point binning, W1 mixes, the one-pass kernel
+// ---------------------------------------------------------------------------
+int bin_setup(const cs_problem* pb, cs::BinParams& b) {
+    if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
+    if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
+    if (pb->P < 0) return fail(CS_EINVAL, "negative size");
+    if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
+    if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
+    if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
+    if (pb->P >= (1ll << 31)) return fail(CS_EUNSUPPORTED, "cs_bin_points: at most 2^31 - 1 points per call (%lld)", (long long)pb->P);
+    memset(&b, 0, sizeof(b));
+    b.dim = pb->dim;
+    b.size[0] = pb->W; b.size[1] = pb->H; b.size[2] = pb->D;
+    b.P = pb->P;
+    b.align = pb->align_corners; b.multicell = pb->multicell; b.index_mode = pb->index_mode;
+    for (int shift = 0;; ++shift) {
+        const int tl = (pb->dim == 2) ? 3 : 2;       // log2 tile edge
+        const long long nx = ((((long long)pb->W - 1) >> shift) >> tl) + 1;
+        const long long ny = ((((long long)pb->H - 1) >> shift) >> tl) + 1;
+        const long long nz = (pb->dim == 3) ? ((((long long)pb->D - 1) >> shift) >> tl) + 1 : 1;
+        const long long nb = nx * ny * nz * 64;
+        if (nb <= (1ll << 21)) {
+            b.shift = shift; b.ntx = (int)nx; b.nty = (int)ny; b.ntz = (int)nz; b.nbins = (unsigned)nb;
+            break;
+        }
+    }
+    return 0;
+}
+
+inline long long round256(long long v) { return (v + 255) / 256 * 256; }
+
+template <int K>
+int premix_launch(const float* V, const float* W1, float* Vh, int C, long long T, long long NT, cudaStream_t s) {
+    const size_t smem = (size_t)C * K * sizeof(float);
+    long long blocks = (NT + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cs::cs_head_premix_kernel<K><<<(unsigned)blocks, 256, smem, s>>>(V, W1, Vh, C, T, NT);
+    return 0;
+}
+
+template <int K, bool KFIRST>
+cudaError_t postmix_launch(const float* gVh, const float* V, const float* W1, float* gInput, int accumulate,
+                           float* gW1, int N, int C, long long T, cudaStream_t s) {
+    auto kern = cs::cs_head_postmix_kernel<K, KFIRST>;
+    const size_t smem = (size_t)(C * K + cs::POSTMIX_TT * (K + 1) + C * cs::POSTMIX_TT) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tpc = (T + cs::POSTMIX_TT - 1) / cs::POSTMIX_TT;
+    const long long ntiles = tpc * N;
+    long long blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
+    kern<<<(unsigned)blocks, cs::POSTMIX_TT, smem, s>>>(gVh, V, W1, gInput, accumulate, gW1, C, T, tpc, ntiles);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -477,6 +538,156 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float* jets, const
     p.vec = (P % 4 == 0) && aligned16(jets) && aligned16(gJets);
     cudaError_t e = cs::launch_head_any(dim, C, p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "pde head kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+
+int cs_bin_workspace_bytes(const cs_problem* pb, int64_t* bytes) {
+    cs::BinParams b;
+    if (int rc = bin_setup(pb, b)) return rc;
+    if (!bytes) return fail(CS_EINVAL, "cs_bin_workspace_bytes: bytes is NULL");
+    *bytes = round256((long long)b.nbins * 4) + round256((long long)pb->P * 4);
+    return 0;
+}
+
+int cs_bin_points(const cs_problem* pb, const float* coords, const float* offset, float* sorted, int32_t* perm,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+    cs::BinParams b;
+    if (int rc = bin_setup(pb, b)) return rc;
+    if (pb->P == 0) return 0;
+    if (!coords || !sorted || !workspace) return fail(CS_EINVAL, "cs_bin_points: NULL pointer");
+    if (coords == sorted) return fail(CS_EINVAL, "cs_bin_points: sorted must not alias coords");
+    const long long hist_bytes = round256((long long)b.nbins * 4);
+    if (workspace_bytes < hist_bytes + round256((long long)pb->P * 4))
+        return fail(CS_EINVAL, "cs_bin_points: workspace too small (see cs_bin_workspace_bytes)");
+    b.coords = coords; b.offset = offset;
+    unsigned* hist = reinterpret_cast<unsigned*>(workspace);
+    unsigned* rank = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)b.nbins * 4, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points memset");
+    long long blocks = (pb->P + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cs::cs_bin_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, rank);
+    cs::cs_bin_scan_kernel<<<1, 1024, 0, s>>>(hist, b.nbins);
+    cs::cs_bin_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, rank, sorted, perm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points launch");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return 0;
+}
+
+static int mix_check(int32_t N, int32_t C, int64_t T, int32_t K) {
+    if (N < 0 || C < 0 || T < 0) return fail(CS_EINVAL, "negative size");
+    if (!(K == 4 || K == 8 || K == 16 || K == 32)) return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16 or 32, got %d", K);
+    if (C > 64) return fail(CS_EUNSUPPORTED, "the W1 mixes support at most 64 input channels, got %d", C);
+    return 0;
+}
+
+int cs_head_premix(int32_t N, int32_t C, int64_t T, int32_t K, const float* input, const float* W1, float* Vh,
+                   void* stream) {
+    if (int rc = mix_check(N, C, T, K)) return rc;
+    if (N == 0 || C == 0 || T == 0) return 0;
+    if (!input || !W1 || !Vh) return fail(CS_EINVAL, "cs_head_premix: NULL pointer");
+    if (!aligned16(Vh)) return fail(CS_EINVAL, "cs_head_premix: Vh must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long NT = (long long)N * T;
+    switch (K) {
+        case 4: premix_launch<4>(input, W1, Vh, C, T, NT, s); break;
+        case 8: premix_launch<8>(input, W1, Vh, C, T, NT, s); break;
+        case 16: premix_launch<16>(input, W1, Vh, C, T, NT, s); break;
+        default: premix_launch<32>(input, W1, Vh, C, T, NT, s); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "cs_head_premix launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int cs_head_postmix(int32_t N, int32_t C, int64_t T, int32_t K, const float* gVh, int32_t hidden_first,
+                    const float* input, const float* W1, float* gInput, int32_t accumulate, float* gW1,
+                    void* stream) {
+    if (int rc = mix_check(N, C, T, K)) return rc;
+    if (N == 0 || C == 0 || T == 0) return 0;
+    if (!gVh || !input || !W1) return fail(CS_EINVAL, "cs_head_postmix: NULL pointer");
+    if (!gInput && !gW1) return 0;
+    if (!hidden_first && !aligned16(gVh)) return fail(CS_EINVAL, "cs_head_postmix: gVh must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+#define CS_POSTMIX(KK) e = hidden_first ? postmix_launch<KK, true>(gVh, input, W1, gInput, accumulate, gW1, N, C, T, s) \
+                                        : postmix_launch<KK, false>(gVh, input, W1, gInput, accumulate, gW1, N, C, T, s)
+    switch (K) {
+        case 4: CS_POSTMIX(4); break;
+        case 8: CS_POSTMIX(8); break;
+        case 16: CS_POSTMIX(16); break;
+        default: CS_POSTMIX(32); break;
+    }
+#undef CS_POSTMIX
+    if (e != cudaSuccess) return cuda_fail(e, "cs_head_postmix launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords, const float* offset,
+                      const float* b1, const float* w2, const float* b2, const cs_pde_residual* res, float scale,
+                      float* gVh, float* gb1, float* gw2, float* gb2, float* loss_sum, int32_t aggregate,
+                      void* stream) {
+    if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
+    if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
+    if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
+    if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
+    if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
+    if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
+    if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
+    if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
+    if (aggregate < 0 || aggregate > 2) return fail(CS_EINVAL, "aggregate must be 0 (off), 1 (auto) or 2 (force)");
+    if (pb->N == 0 || pb->C == 0 || pb->P == 0) return 0;
+    if (pb->field_layout != CS_LAYOUT_CHANNEL_LAST)
+        return fail(CS_EUNSUPPORTED, "cs_pde_fused_step needs the channel-last mixed cells of cs_head_premix");
+    const int K = pb->C;
+    if (!(K == 4 || K == 8 || K == 16 || K == 32))
+        return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16 or 32, got %d", K);
+    if (!Vh || !coords || !offset || !b1 || !w2 || !b2 || !res || !gVh || !gb1 || !gw2 || !gb2 || !loss_sum)
+        return fail(CS_EINVAL, "cs_pde_fused_step: NULL pointer");
+    if (!aligned16(Vh) || !aligned16(gVh)) return fail(CS_EINVAL, "cs_pde_fused_step: Vh / gVh must be 16-byte aligned");
+    const long long T = (long long)pb->D * pb->H * pb->W;
+    if (T * (long long)K >= (1ll << 31))
+        return fail(CS_EUNSUPPORTED, "a cell has %lld elements; the per-cell index is 32-bit", T * K);
+    if (pb->P >= (1ll << 33)) return fail(CS_EUNSUPPORTED, "too many points (%lld)", (long long)pb->P);
+    cs::FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = pb->N; p.K = K; p.P = pb->P;
+    p.size[0] = pb->W; p.size[1] = pb->H; p.size[2] = pb->D;
+    p.tstride[0] = 1; p.tstride[1] = pb->W; p.tstride[2] = pb->W * pb->H;
+    p.cell_stride = T * K;
+    p.Vh = Vh; p.gVh = gVh; p.coords = coords; p.offset = offset;
+    p.b1 = b1; p.w2 = w2; p.b2 = b2;
+    p.gb1 = gb1; p.gw2 = gw2; p.gb2 = gb2; p.loss_sum = loss_sum;
+    p.c_u = res->c_u; p.c_u3 = res->c_u3;
+    for (int a = 0; a < 3; ++a) { p.c1[a] = res->c1[a]; p.c2[a] = res->c2[a]; }
+    p.scale = scale;
+    p.cvec2 = (reinterpret_cast<uintptr_t>(coords) & 7u) == 0;
+    p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
+    p.multicell = pb->multicell; p.index_mode = pb->index_mode;
+    const int v = K / 4;
+    const int lshift = (v == 1) ? 0 : (v == 2) ? 1 : (v == 4) ? 2 : 3;
+    // aggregation windows: 2D only, and only while 3 warps' worth of them leave room for 2 blocks per SM
+    bool agg = false;
+    if (aggregate && pb->dim == 2) {
+        const int L = 1 << lshift, NW = 32 >> lshift;
+        const long long per_warp = (long long)(3 * 4 * NW + NW * (cs::fused_win_stride(pb->N, L) + pb->N)) * 16;
+        agg = 3 * per_warp <= 110 * 1024;
+        if (!agg && aggregate == 2) return fail(CS_EUNSUPPORTED, "aggregation windows of %d cells do not fit in shared memory", pb->N);
+    } else if (aggregate == 2) {
+        return fail(CS_EUNSUPPORTED, "aggregation windows are implemented for dim == 2");
+    }
+    using Fn = cudaError_t (*)(bool, cs::FusedParams&, cudaStream_t);
+    static const Fn table[2][4] = {
+        {cs::launch_fused_d2_l0, cs::launch_fused_d2_l1, cs::launch_fused_d2_l2, cs::launch_fused_d2_l3},
+        {cs::launch_fused_d3_l0, cs::launch_fused_d3_l1, cs::launch_fused_d3_l2, cs::launch_fused_d3_l3}};
+    cudaError_t e = table[pb->dim - 2][lshift](agg, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fused step kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }

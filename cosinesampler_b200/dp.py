@@ -60,11 +60,25 @@ class PointShardedStep:
         self.fused = fused
         self.reducer = None
         self.loss_is_global = False
+        self.mode = None
+        if fused is not None:
+            from .jet import fused_mode
+            self.mode = fused.get("mode", "auto")
+            if self.mode == "auto":
+                self.mode = fused_mode(cells, head, fused.get("align_corners", True))
         if peer_reduce and fused is not None and dist.is_available() and dist.is_initialized() \
                 and dist.get_world_size(group) > 1:
-            from .jet import head_buffer_size
             from .peer import PeerReducer
-            self.reducer = PeerReducer(cells, head_buffer_size(cells.shape[1]), group)
+            if self.mode == "onepass":
+                # the one-pass step scatters into the W1-mixed cells: K hidden units per texel
+                from .fused import head_params, small_buffer_size
+                K = head_params(head, cells.shape[1])[0].shape[0]
+                self.reducer = PeerReducer(cells, small_buffer_size(cells.shape[1], K), group, channels=K)
+            elif self.mode == "jets":
+                from .jet import head_buffer_size
+                self.reducer = PeerReducer(cells, head_buffer_size(cells.shape[1]), group)
+            else:
+                raise NotImplementedError("the peer-memory reduce needs a fused head")
             self.loss_is_global = True
 
     def params(self):
@@ -78,9 +92,10 @@ class PointShardedStep:
         if self.fused is not None:
             from .jet import fused_pde_step
             xy = local_coords if torch.is_tensor(local_coords) else torch.cat(list(local_coords), -1)
+            kw = dict(self.fused)
+            kw["mode"] = self.mode
             loss = fused_pde_step(self.cells, xy.contiguous(), self.head, self.residual, chunk=self.chunk,
-                                  loss_scale=xy.shape[0] / float(total_points), reducer=self.reducer,
-                                  **self.fused)
+                                  loss_scale=xy.shape[0] / float(total_points), reducer=self.reducer, **kw)
             if self.reducer is None:
                 allreduce_grads(self.params(), self.group)
             return loss

@@ -345,13 +345,20 @@ class FusedPdeStep:
         self.residual, self.k2 = residual, k2
         self.pm = padding_mode_enum(padding_mode)
         self.kn = _require_kernel(_kernel_enum(kernel, "bilinear" if self.dim == 2 else "trilinear"), kernel)
+        if self.dim == 2 and not align_corners:
+            raise NotImplementedError(
+                "2D with align_corners=False: the reference's 2D forward ignores the flag (cu2d:307-308) while its "
+                "backward kernels honour it; the fused step refuses that inconsistent combination "
+                "(SamplerJet2d honours the flag consistently and says so)")
         self.align_corners, self.multicell = align_corners, multicell
         self.params = _head_params(head, cells.shape[1])
         self._live = False
 
-    def begin(self, reducer=None):
+    def begin(self, reducer=None, scale=None):
         """reducer: a `peer.PeerReducer` whose symmetric-memory accumulators receive the scatters, so
-        that `finish` can sum over the ranks with one kernel over NVLink instead of NCCL."""
+        that `finish` can sum over the ranks with one kernel over NVLink instead of NCCL.
+        scale: the step's loss scale, when known up front (a rank whose shard is empty never calls `add`
+        but must still scale the reduced loss like the others)."""
         with torch.no_grad():
             self.cells_d = self.cells.detach()
             self.offset = cell_offsets(self.cells.shape[0], self.multicell, self.cells.device)
@@ -364,7 +371,7 @@ class FusedPdeStep:
                 self.acc = new_accumulator(self.cells_d)
                 # the head kernel adds into this buffer: loss and head gradients of all chunks, no torch ops
                 self.buf = head_buffer(self.cells.shape[1], self.cells.device)
-        self.scale, self._live = None, True
+        self.scale, self._live = (None if scale is None else float(scale)), True
 
     def add(self, xy, scale):
         """One chunk of points xy [p, dim]; its loss contribution is scale * sum_p f^2 (the same
@@ -441,27 +448,63 @@ def jet_autograd_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2
     return total if total is not None else torch.zeros((), device=cells.device)
 
 
+_warned_fallback = set()
+
+
+def fused_mode(cells, head, align_corners=True):
+    """Which implementation `fused_pde_step(mode='auto')` takes for this head:
+    'onepass' (`fused.OnePassPdeStep`: Linear(C,K)-Tanh-Linear(K,1), K in {4,8,16,32}; one kernel per chunk),
+    'jets' (`FusedPdeStep`: jets -> tensor-core head -> scatter, Linear(C,16)-Tanh-Linear(16,1)), or
+    'torch_head' (`jet_autograd_step`: jet kernels + the head's chain rule in torch ops)."""
+    from . import fused
+    C = cells.shape[1]
+    if fused.head_is_fusable(head, C) and (cells.dim() == 5 or align_corners):
+        return "onepass"
+    if head_is_fusable(head, C) and C in SUPPORTED_CHANNELS:
+        return "jets"
+    return "torch_head"
+
+
 def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
-                   align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0, reducer=None):
-    """`FusedPdeStep` over coords [P, dim] in chunks of `chunk` points: accumulates `cells.grad` and the
-    head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor.  Heads other than
-    Linear(C,16)-Tanh-Linear(16,1) take `jet_autograd_step` (jet kernels + torch head) instead."""
+                   align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0, reducer=None,
+                   mode="auto"):
+    """One training step over coords [P, dim] in chunks of `chunk` points without nested autograd:
+    accumulates `cells.grad` and the head parameters' `.grad`, returns loss_scale * mean_p f^2 as a
+    0-dim tensor.  mode: 'auto' (see `fused_mode`), 'onepass', 'jets' or 'torch_head'.  Falling back to
+    the torch head is announced once per head shape (it is several times slower)."""
     ops._check(cells, "input")
-    if cells.dim() in (4, 5) and not head_is_fusable(head, cells.shape[1]):
+    if cells.dim() not in (4, 5):
+        raise RuntimeError("expected cells [N,C,(D,)H,W], got %s" % (tuple(cells.shape),))
+    if mode == "auto":
+        mode = fused_mode(cells, head, align_corners)
+        if mode == "torch_head":
+            key = tuple((type(l).__name__, getattr(l, "in_features", 0), getattr(l, "out_features", 0)) for l in head)
+            if key not in _warned_fallback:
+                _warned_fallback.add(key)
+                import warnings
+                warnings.warn("cosinesampler_b200: head %s is not Linear(C,K)-Tanh-Linear(K,1) with K in {4,8,16,32}; "
+                              "fused_pde_step runs the jet kernels with the head in torch ops (slower)" % (key,))
+    if mode == "onepass":
+        from . import fused
+        return fused.one_pass_pde_step(cells, coords, head, residual, k2, padding_mode, align_corners, kernel,
+                                       multicell, chunk, loss_scale, reducer)
+    if mode == "torch_head":
         if reducer is not None:
-            raise NotImplementedError("the peer-memory reduce needs the fused head")
+            raise NotImplementedError("the peer-memory reduce needs a fused head")
         return jet_autograd_step(cells, coords, head, residual, k2, padding_mode, align_corners, kernel,
                                  multicell, chunk, loss_scale)
+    if mode != "jets":
+        raise ValueError("mode must be 'auto', 'onepass', 'jets' or 'torch_head', got %r" % (mode,))
     step = FusedPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell)
     P = coords.shape[0]
     chunk = max(1, P if not chunk else min(chunk, P))
-    step.begin(reducer)
+    step.begin(reducer, scale=loss_scale / P if P else 0.0)
     for s in range(0, P, chunk):
         step.add(coords[s:s + chunk], loss_scale / P)
     return step.finish()
 
 
-__all__ = ["SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
+__all__ = ["fused_mode", "SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
            "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "FusedPdeStep", "jet_autograd_step",
            "head_is_fusable",
            "residual_coefficients"]

@@ -23,7 +23,9 @@ MAX_PEERS = 8
 class PeerReducer:
     """Symmetric buffers + the fused reduce for one `cells` shape and one process group."""
 
-    def __init__(self, cells, n_small, group=None):
+    def __init__(self, cells, n_small, group=None, channels=None):
+        """channels: channel count of the accumulator when it differs from the cells' (the one-pass step
+        scatters into the W1-mixed cells: K hidden units per texel instead of C channels)."""
         import torch.distributed._symmetric_memory as symm_mem
         if not dist.is_initialized():
             raise RuntimeError("PeerReducer needs an initialised process group")
@@ -32,8 +34,9 @@ class PeerReducer:
         if self.world > MAX_PEERS:
             raise RuntimeError("PeerReducer supports at most %d ranks, got %d" % (MAX_PEERS, self.world))
         ops._check(cells, "input")
-        self.shape = tuple(cells.shape)
-        self.N, self.C = cells.shape[:2]
+        self.N = cells.shape[0]
+        self.C = int(channels) if channels is not None else cells.shape[1]
+        self.shape = (self.N, self.C) + tuple(cells.shape[2:])
         self.T = cells[0, 0].numel()
         self.n_small = int(n_small)
         dev = cells.device

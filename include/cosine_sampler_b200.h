@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CS_VERSION 100
+#define CS_VERSION 200
 
 /* padding_mode_enum, modules_2d.py:4-10 */
 #define CS_PAD_ZEROS 0
@@ -160,6 +160,47 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float *jets, const
                      const float *w2, const float *b2, const cs_pde_residual *res, float scale,
                      float *gJets, float *gW1, float *gb1, float *gw2, float *gb2, float *loss_sum,
                      float *f_out, void *stream);
+
+/* ---- One-pass fused training step (not in the reference; SURVEY section 8f ranks 1 + 2) ------------------
+ * For a head Linear(C,K)-Tanh-Linear(K,1) the whole step of test_2d.py:36-127 -- replicate, sample, sum over
+ * cells, head, nested autograd for u_a / u_aa, residual, loss, and the triple-backward scatters of
+ * modules_2d.py:98-111 -- is ONE pass over the points.  The sampler and the head's first layer are both
+ * linear, so they commute: the cells are mixed with W1 once per step (cs_head_premix), the gather then
+ * delivers the hidden pre-activations, the adjoint scatters d loss / d hidden into gVh, and cs_head_postmix
+ * returns gInput = W1^T gVh and gW1 = sum_texels gVh (x) input.  Points may be given in any order; binned
+ * by texel (cs_bin_points) the kernel gathers from cache and pre-reduces its scatter in shared memory. */
+
+/* Counting sort of coords [P, dim] on a tile-major texel key (8x8 texels in 2D, 4x4x4 in 3D) of cell 0.
+ * sorted [P, dim]; perm [P] (nullable): perm[i] = index in coords of sorted point i.  offset [N] device
+ * (nullable).  workspace: cs_bin_workspace_bytes() bytes of device scratch.  Order inside a bin is not
+ * deterministic.  Uses pb->dim, D/H/W, P, align_corners, multicell, index_mode. */
+int cs_bin_workspace_bytes(const cs_problem *pb, int64_t *bytes);
+int cs_bin_points(const cs_problem *pb, const float *coords, const float *offset, float *sorted,
+                  int32_t *perm, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Vh [N, T, K] = W1 [K, C] applied to input [N, C, T] texel by texel (channel-first in, channel-last out:
+ * the staging transpose and the first Linear layer, test_2d.py:44, in one pass).  K in {4, 8, 16, 32}, C <= 64. */
+int cs_head_premix(int32_t N, int32_t C, int64_t T, int32_t K, const float *input, const float *W1,
+                   float *Vh, void *stream);
+/* gInput [N, C, T] (= or +=, nullable) = W1^T gVh;  gW1 [K, C] (+=, nullable) = sum_{n,t} gVh[n,t,:] (x) input[n,:,t].
+ * gVh is [N, T, K] (hidden_first = 0) or [N, K, T] (hidden_first = 1: the output of
+ * cs_peer_allreduce_from_channel_last). */
+int cs_head_postmix(int32_t N, int32_t C, int64_t T, int32_t K, const float *gVh, int32_t hidden_first,
+                    const float *input, const float *W1, float *gInput, int32_t accumulate, float *gW1,
+                    void *stream);
+
+/* The pass itself.  pb describes the MIXED cells: pb->C = K (hidden width, in {4, 8, 16, 32}),
+ * pb->field_layout = CS_LAYOUT_CHANNEL_LAST, P = number of points; coords [P, dim] shared by all cells.
+ * Residual f = c_u u + c_u3 u^3 + sum_a (c1[a] u_a + c2[a] u_aa) with u = w2 . tanh(H + b1) + b2 and H the
+ * sampled mixed cells summed over the N cells; loss_sum [1] += sum_p f^2 (unscaled); gradients of
+ * scale * sum_p f^2: gVh [N, T, K] += (zero-initialised by the caller), gb1 [K] +=, gw2 [K] +=, gb2 [1] +=.
+ * aggregate: 0 = one red.global.add.v4.f32 per (cell, point, corner); 1 = auto: walker-private 3x3-texel
+ * windows in shared memory when dim == 2 and they fit (meant for binned points); 2 = require them. */
+struct cs_pde_residual;
+int cs_pde_fused_step(const cs_problem *pb, const float *Vh, const float *coords, const float *offset,
+                      const float *b1, const float *w2, const float *b2, const struct cs_pde_residual *res,
+                      float scale, float *gVh, float *gb1, float *gw2, float *gb2, float *loss_sum,
+                      int32_t aggregate, void *stream);
 
 /* ---- Gradient all-reduce over peer memory, fused with the layout change ------------
  * acc_ptrs[r] / out_ptrs[r] (r < world <= CS_MAX_PEERS): device addresses, valid on THIS device, of rank r's

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None, name
-    assert lib.cs_version() == 100
+    assert lib.cs_version() == 200
     assert lib.cs_launch_count() == 0 or lib.cs_launch_count() > 0   # callable without a GPU
 
 
