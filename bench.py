@@ -44,19 +44,22 @@ CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tenso
 
 
 def ncu_traffic_bytes(label):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a stage kernel, from the committed
-    `ncu --set full` capture of the same shapes (profiles/r1/ncu_stages_cfg{3,4}_summary.json; the
-    fused kernels: ncu_fused_cfg{3,4}_summary.json, captured at 2^20 / 2^22 points per launch)."""
-    for name in ("ncu_stages_cfg3_summary.json", "ncu_stages_cfg4_summary.json",
-                 "ncu_fused_cfg3_summary.json", "ncu_fused_cfg4_summary.json"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed
+    `ncu --set full` captures of the same shapes (profiles/r2/*_summary.json, else profiles/r1/...; the
+    captures drive the same call pattern as this bench: an expanded gOut for the stage kernels, 2^22
+    binned points per launch for the one-pass kernel).  -> (bytes, points per launch of the capture)"""
+    for rnd, name in (("r2", "ncu_stages_cfg3_summary.json"), ("r2", "ncu_stages_cfg4_summary.json"),
+                      ("r2", "ncu_onepass_cfg3_summary.json"), ("r2", "ncu_onepass_cfg4_summary.json"),
+                      ("r1", "ncu_stages_cfg3_summary.json"), ("r1", "ncu_stages_cfg4_summary.json"),
+                      ("r1", "ncu_fused_cfg3_summary.json"), ("r1", "ncu_fused_cfg4_summary.json")):
         try:
-            with open(os.path.join(ROOT, "profiles", "r1", name)) as f:
-                kernels = json.load(f)["kernels"]
-            if label in kernels:
-                return int(kernels[label]["traffic_bytes"])
+            with open(os.path.join(ROOT, "profiles", rnd, name)) as f:
+                doc = json.load(f)
+            if label in doc["kernels"]:
+                return int(doc["kernels"][label]["traffic_bytes"]), doc.get("points_per_launch"), "profiles/%s/%s" % (rnd, name)
         except Exception:
             pass
-    return None
+    return None, None, None
 
 
 def measured_peak_gbs():
@@ -120,29 +123,53 @@ class ClockSampler:
 
 
 class StageProfiler:
-    """Collects CUDA-event timings of every stage call issued inside the timed region."""
+    """Collects CUDA-event timings of every kernel bracket (ops._timed) issued inside the timed region."""
 
     def __init__(self):
         self.records = []
 
-    def record(self, label, nbytes, start, end):
-        self.records.append((label, nbytes, start, end))
+    def record(self, label, nbytes, start, end, moved=None):
+        self.records.append((label, nbytes, start, end, nbytes if moved is None else moved))
 
     def summary(self):
         agg = {}
-        for label, nbytes, s, e in self.records:
-            a = agg.setdefault(label, [0, 0.0, 0])
+        for label, nbytes, s, e, moved in self.records:
+            a = agg.setdefault(label, [0, 0.0, 0, 0])
             a[0] += 1
             a[1] += s.elapsed_time(e)
             a[2] += nbytes
+            a[3] += moved
         return {k: {"launches": v[0], "ms_total": v[1], "ms_avg": v[1] / v[0],
-                    "bytes_per_launch": v[2] // v[0]} for k, v in agg.items()}
+                    "bytes_per_launch": v[2] // v[0], "moved_per_launch": v[3] // v[0]} for k, v in agg.items()}
+
+
+def stage_table(stage, peak):
+    return {k: {"launches": v["launches"], "ms_avg": round(v["ms_avg"], 4),
+                "GBps": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9, 1),
+                "frac": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9 / peak, 4),
+                "frac_as_moved": round(v["moved_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9 / peak, 4)}
+            for k, v in sorted(stage.items())}
+
+
+def kernel_roofline(stage, top, peak, peak_src, ms_step_total, points_per_launch=None):
+    v = stage[top]
+    a = v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9
+    m = v["moved_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9
+    traffic, cap_points, src = ncu_traffic_bytes(top)
+    if traffic is not None and cap_points and points_per_launch:
+        traffic = int(traffic * points_per_launch / float(cap_points))
+    return {"kernel": top, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(a / peak, 4), "achieved_as_moved": round(m, 1), "frac_as_moved": round(m / peak, 4),
+            "traffic": traffic, "traffic_source": src, "peak_source": peak_src,
+            "launches": v["launches"], "ms_avg": round(v["ms_avg"], 4), "bytes_per_launch": v["bytes_per_launch"],
+            "moved_per_launch": v["moved_per_launch"], "share_of_step": round(v["ms_total"] / ms_step_total, 4)}
 
 
 # ---------------------------------------------------------------------------------------
-def make_inputs(workload, rank, world, device, dtype):
+def make_inputs(workload, rank, world, device, dtype, total=None):
     import torch
-    dim, shape, total, chunk, kernel, residual = WORKLOADS[workload]
+    dim, shape, wtotal, chunk, kernel, residual = WORKLOADS[workload]
+    total = total or wtotal
     from cosinesampler_b200 import chain, dp
     g = torch.Generator().manual_seed(0)
     cells = torch.rand(shape, generator=g, dtype=dtype)                 # U(0,1), replicated
@@ -153,65 +180,66 @@ def make_inputs(workload, rank, world, device, dtype):
     return cells, coords_host, head
 
 
-def run_ours(args):
+def measure_workload(args, workload, steps, warmup, ctx, with_jets):
+    """All ranks run this; rank 0 gets the result dictionary (others None)."""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
-                         "(use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from cosinesampler_b200 import _lib, chain, dp, ops
+    from cosinesampler_b200 import _lib, chain, dp, fused, jet, ops
     from cosine_sampler_2d import CosineSampler2d
     from cosine_sampler_3d import CosineSampler3d
+    rank, world, device = ctx["rank"], ctx["world"], ctx["device"]
 
-    dim, shape, total, chunk, kernel, residual = WORKLOADS[args.workload]
-    if args.points:
+    dim, shape, total, chunk, kernel, residual = WORKLOADS[workload]
+    if args.points and workload == args.workload:
         total = args.points
     N, C = shape[:2]
     S = CosineSampler2d if dim == 2 else CosineSampler3d
     sampler = lambda c, g: S.apply(c, g, "zeros", True, kernel, True)
-    cells_h, coords_host, head = make_inputs(args.workload, rank, world, device, torch.float32)
-    if args.points:
-        s, e = dp.shard_range(total, rank, world)
-        coords_host = coords_host[: e - s]
+    cells_h, coords_host, head = make_inputs(workload, rank, world, device, torch.float32, total)
     cells = torch.nn.Parameter(cells_h.to(device))
     coords_pinned = coords_host.pin_memory()
     coords_dev = coords_host.to(device)
+    nloc = coords_host.shape[0]
     stepper = dp.PointShardedStep(sampler, cells, head, residual=residual, chunk=chunk)
-    from cosinesampler_b200 import jet
     fused_kw = dict(kernel=kernel, multicell=True)
-    # the fused step keeps [1+2*dim, C, chunk] jets instead of [N, C, chunk] streams: 4x the chunk of
-    # the drop-in arm is the same footprint per stream
-    fchunk = 4 * chunk
+    # the one-pass step keeps nothing per point but the coordinates: a whole shard is one chunk (the more points
+    # a chunk holds, the more of them share a texel and the fewer reds leave the SMs); the end-to-end arm cuts
+    # the shard into pieces so that the host->device copy of one piece overlaps the pass over the previous one
+    fchunk = max(1, nloc)
+    fchunk_e2e = max(2 ** 20, (nloc + 3) // 4)
     reduce_kind = "none (single GPU)"
     fstepper = None
-    if world > 1 and not args.nccl_reduce:
-        try:        # gradient reduce fused with the layout change over NVLink peer memory (peer.py)
+    want_peer = world > 1 and not args.nccl_reduce
+    if want_peer:
+        # all ranks must take the same path: vote BEFORE the collective rendezvous of the reducer
+        ok = 1.0
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception as exc:
+            print("symmetric memory unavailable (%s); using NCCL" % exc, file=sys.stderr)
+            ok = 0.0
+        vote = torch.tensor([ok], device=device)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if float(vote.item()) > 0.5:
             fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw,
                                            peer_reduce=True)
             reduce_kind = "peer-memory kernel cs_peer_allreduce_from_channel_last (symmetric memory over NVLink)"
-        except Exception as exc:          # no symmetric memory on this box: NCCL
-            print("peer-memory reduce unavailable (%s); using NCCL" % exc, file=sys.stderr)
-            fstepper = None
-        # all ranks must take the same path: one vote, NCCL unless every rank has its reducer
-        vote = torch.tensor([1.0 if fstepper is not None else 0.0], device=device)
-        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
-        if float(vote.item()) < 0.5:
-            fstepper = None
     if fstepper is None:
         fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
         if world > 1:
             reduce_kind = "NCCL all-reduce of one flat bucket"
+    jstepper = None
+    if with_jets and world == 1:
+        jstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=4 * chunk,
+                                       fused=dict(fused_kw, mode="jets"))
 
     def fused_resident():
         fstepper.zero_grad()
         return fstepper.step(coords_dev, total)
+
+    def jets_resident():
+        jstepper.zero_grad()
+        return jstepper.step(coords_dev, total)
 
     def step_resident():
         stepper.zero_grad()
@@ -219,25 +247,22 @@ def run_ours(args):
         return stepper.step(cols, total)
 
     loss_host = torch.zeros(1, pin_memory=True)
-
     copy_stream = torch.cuda.Stream(device=device)
+
+    def fetch(span):
+        with torch.cuda.stream(copy_stream):
+            t = coords_pinned[span[0]:span[1]].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return t, ev
 
     def step_e2e():
         """Same step from HOST buffers: every chunk of coordinates is copied from pinned host
         memory inside the timed region (on a copy stream, one chunk ahead of the compute stream) and
         the step's loss is read back to the host."""
         stepper.zero_grad()
-        nloc = coords_pinned.shape[0]
         spans = [(s0, min(nloc, s0 + chunk)) for s0 in range(0, nloc, chunk)]
         cur = torch.cuda.current_stream()
-
-        def fetch(span):
-            with torch.cuda.stream(copy_stream):
-                t = coords_pinned[span[0]:span[1]].to(device, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return t, ev
-
         nxt = fetch(spans[0])
         acc = None
         for i, span in enumerate(spans):
@@ -257,19 +282,13 @@ def run_ours(args):
     def fused_e2e():
         """The fused step from HOST buffers, same copy pipeline as step_e2e."""
         fstepper.zero_grad()
-        nloc = coords_pinned.shape[0]
-        spans = [(s0, min(nloc, s0 + fchunk)) for s0 in range(0, nloc, fchunk)]
+        spans = [(s0, min(nloc, s0 + fchunk_e2e)) for s0 in range(0, nloc, fchunk_e2e)]
         cur = torch.cuda.current_stream()
-
-        def fetch(span):
-            with torch.cuda.stream(copy_stream):
-                t = coords_pinned[span[0]:span[1]].to(device, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return t, ev
-
-        fs = jet.FusedPdeStep(cells, head, residual, kernel=kernel, multicell=True)
-        fs.begin(fstepper.reducer)
+        if fstepper.mode == "onepass":
+            fs = fused.OnePassPdeStep(cells, head, residual, kernel=kernel, multicell=True)
+        else:
+            fs = jet.FusedPdeStep(cells, head, residual, kernel=kernel, multicell=True)
+        fs.begin(fstepper.reducer, scale=1.0 / float(total))
         nxt = fetch(spans[0])
         for i, span in enumerate(spans):
             t, ev = nxt
@@ -290,12 +309,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(steps):
+        for _ in range(nsteps):
             fn()
         t1.record()
         barrier()
@@ -304,17 +323,17 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(args.warmup):
+    # ---- the drop-in operator (the reference's API; what PIXEL runs unchanged)
+    for _ in range(warmup):
         step_resident()
     barrier()
-
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(ctx["local"])
     prof = StageProfiler()
     if rank == 0:
         clocks.start()
     ops.profiler = prof
     n0 = _lib.launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, steps)
     launches = _lib.launch_count() - n0
     ops.profiler = None
     clock_info = clocks.stop() if rank == 0 else None
@@ -322,110 +341,144 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(loss_t)                      # each rank holds its share of the mean
     loss_val = float(loss_t.item())
-
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 2))):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
 
-    # ---- the opt-in fused jet path (jet.FusedPdeStep), same inputs, same outputs
-    for _ in range(args.warmup):
+    # ---- the opt-in fused step, same inputs, same outputs
+    for _ in range(warmup):
         fused_resident()
     barrier()
     fprof = StageProfiler()
     ops.profiler = fprof
     n0 = _lib.launch_count()
-    ms_f = timed(fused_resident, args.steps)
+    ms_f = timed(fused_resident, steps)
     flaunches = _lib.launch_count() - n0
     ops.profiler = None
     floss_t = fused_resident().detach().clone()
     if world > 1 and not fstepper.loss_is_global:
         dist.all_reduce(floss_t)
     floss_val = float(floss_t.item())
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 2))):
         fused_e2e()
-    ms_f_e2e = timed(fused_e2e, args.steps)
+    ms_f_e2e = timed(fused_e2e, steps)
+    ms_j = None
+    if jstepper is not None:
+        for _ in range(2):
+            jets_resident()
+        ms_j = timed(jets_resident, 2) / 2
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src = measured_peak_gbs()
-    pts_per_s = total * args.steps / (ms * 1e-3)
-    e2e_pts_per_s = total * args.steps / (ms_e2e * 1e-3)
     stage = prof.summary()
-    top = max(stage, key=lambda k: stage[k]["ms_total"]) if stage else None
-    roofline = None
-    if top:
-        a = stage[top]["bytes_per_launch"] / (stage[top]["ms_avg"] * 1e-3) / 1e9
-        roofline = {"kernel": top, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(a / peak, 4), "traffic": ncu_traffic_bytes(top), "peak_source": peak_src,
-                    "launches": stage[top]["launches"], "ms_avg": round(stage[top]["ms_avg"], 4),
-                    "bytes_per_launch": stage[top]["bytes_per_launch"],
-                    "share_of_step": round(stage[top]["ms_total"] / ms, 4)}
-    G = 4 * N * C * (shape[2] * shape[3] * (shape[4] if dim == 3 else 1))
-    chain_bytes = total * N * CHAIN_BYTES_PER_PAIR[args.workload] + \
-        CHAIN_FIELD_TERMS[args.workload] * G * math.ceil(total / world / chunk) * world
-    chain_gbs = chain_bytes * args.steps / (ms * 1e-3) / 1e9 / world
+    sampler_ms = sum(v["ms_total"] for v in stage.values()) / steps
+    kernel_stages = {k: v for k, v in stage.items() if not k.startswith("AUX")}
+    top = max(kernel_stages, key=lambda k: kernel_stages[k]["ms_total"]) if kernel_stages else None
+    T = 1
+    for s_ in shape[2:]:
+        T *= s_
+    G = 4 * N * C * T
+    chain_bytes = total * N * CHAIN_BYTES_PER_PAIR[workload] + \
+        CHAIN_FIELD_TERMS[workload] * G * math.ceil(total / world / chunk) * world
+    chain_gbs = chain_bytes * steps / (ms * 1e-3) / 1e9 / world
+    sampler_gbs = chain_bytes / world / (sampler_ms * 1e-3) / 1e9
+    wl = "%s: cells %s, %d points total, chunk %d, kernel %s, multicell, residual %s" \
+        % (workload, list(shape), total, chunk, kernel, residual)
     out = {
         "metric": "points/s fwd->triple-bwd (PIXEL Helmholtz step, 2D cosine multicell)"
                   if dim == 2 else "points/s fwd->triple-bwd (3D smoothstep multicell Laplacian step)",
-        "value": pts_per_s, "unit": "points/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "value": total * steps / (ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: cells %s, %d points total, chunk %d, kernel %s, multicell, residual %s"
-                               % (args.workload, list(shape), total, chunk, kernel, residual),
-                   "points_per_rank": coords_host.shape[0], "parallelism": "dp%d over points" % world,
+        "config": {"workload": wl, "points_per_rank": nloc, "parallelism": "dp%d over points" % world,
                    "l2": "inputs larger than L2 (each [N,C,P] stream of a chunk is %d MiB)"
                          % (4 * N * C * min(chunk, total) // 2 ** 20)},
-        "e2e": {"value": e2e_pts_per_s, "unit": "points/s",
+        "e2e": {"value": total * steps / (ms_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": roofline,
+        "roofline": kernel_roofline(stage, top, peak, peak_src, ms) if top else None,
         "chain_roofline": {"bound": "hbm", "bytes_per_step_minimal": chain_bytes,
                            "achieved": round(chain_gbs, 1), "peak": peak, "unit": "GB/s per GPU",
-                           "frac": round(chain_gbs / peak, 4)},
-        "stages": {k: {"launches": v["launches"], "ms_avg": round(v["ms_avg"], 4),
-                       "GBps": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9, 1)}
-                   for k, v in sorted(stage.items())},
+                           "frac": round(chain_gbs / peak, 4),
+                           "note": "BASELINE.md's minimal bytes of the step over the whole step time, the "
+                                   "caller's torch head included"},
+        "sampler_only": {"ms_per_step": round(sampler_ms, 4),
+                         "ms_per_2^20_points": round(sampler_ms * 2 ** 20 * world / total, 4),
+                         "achieved": round(sampler_gbs, 1), "unit": "GB/s per GPU",
+                         "frac": round(sampler_gbs / peak, 4),
+                         "share_of_step": round(sampler_ms / (ms / steps), 4),
+                         "note": "sum of the CUDA-event brackets of every kernel this library launches in a step "
+                                 "(stage kernels + accumulator memsets + layout transposes), BASELINE.md's "
+                                 "minimal bytes over that time: the operator's own roofline fraction"},
+        "stages": stage_table(stage, peak),
         "loss": loss_val,
         "index_mode": ops.get_index_mode(),
     }
     fstage = fprof.summary()
-    ftop = max(fstage, key=lambda k: fstage[k]["ms_total"]) if fstage else None
-    fchain_gbs = chain_bytes * args.steps / (ms_f * 1e-3) / 1e9 / world
+    fkern = {k: v for k, v in fstage.items() if k.startswith("ONEPASS") or k.startswith("JET") or k.startswith("HEAD")}
+    ftop = max(fkern, key=lambda k: fkern[k]["ms_total"]) if fkern else None
+    fchain_gbs = chain_bytes * steps / (ms_f * 1e-3) / 1e9 / world
     out["fused"] = {
-        "api": "cosinesampler_b200.jet.FusedPdeStep (opt-in; SURVEY 8f ranks 1+2): jets in one gather pass, "
-               "head + residual + gradients in one kernel, one scatter pass; same loss and gradients",
-        "chunk": fchunk, "gradient_reduce": reduce_kind,
-        "value": total * args.steps / (ms_f * 1e-3), "unit": "points/s", "ms_per_step": ms_f / args.steps,
-        "e2e": {"value": total * args.steps / (ms_f_e2e * 1e-3), "unit": "points/s",
+        "api": "cosinesampler_b200.fused.OnePassPdeStep (opt-in; SURVEY 8f ranks 1+2): cells mixed with the head's first "
+               "layer once per step, points binned by texel, gather -> tanh / residual / gradients -> scatter in ONE "
+               "kernel, register-aggregated reds; same loss and gradients" if fstepper.mode == "onepass" else
+               "cosinesampler_b200.jet.FusedPdeStep (jets -> tensor-core head -> scatter)",
+        "mode": fstepper.mode, "chunk": fchunk, "chunk_e2e": fchunk_e2e, "gradient_reduce": reduce_kind,
+        "value": total * steps / (ms_f * 1e-3), "unit": "points/s", "ms_per_step": ms_f / steps,
+        "ms_per_2^20_points": round(ms_f / steps * 2 ** 20 * world / total, 4),
+        "e2e": {"value": total * steps / (ms_f_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_f_e2e / args.steps},
+                "ms_per_step": ms_f_e2e / steps},
         "gpu_launches": int(flaunches), "loss": floss_val,
         "speedup_vs_dropin": ms / ms_f,
-        "stages": {k: {"launches": v["launches"], "ms_avg": round(v["ms_avg"], 4),
-                       "GBps": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9, 1),
-                       "frac": round(v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9 / peak, 4)}
-                   for k, v in sorted(fstage.items())},
-        "roofline": None if not ftop else {
-            "kernel": ftop, "bound": "hbm", "unit": "GB/s", "peak": peak,
-            "achieved": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9, 1),
-            "frac": round(fstage[ftop]["bytes_per_launch"] / (fstage[ftop]["ms_avg"] * 1e-3) / 1e9 / peak, 4),
-            "bytes_per_launch": fstage[ftop]["bytes_per_launch"], "ms_avg": round(fstage[ftop]["ms_avg"], 4),
-            "traffic": None if ncu_traffic_bytes(ftop) is None else int(
-                ncu_traffic_bytes(ftop) * (min(fchunk, coords_host.shape[0]) / float(2 ** 20 if dim == 2 else 2 ** 22))),
-            "traffic_note": "ncu dram bytes of the committed capture, scaled from its points per launch to this run's",
-            "share_of_step": round(fstage[ftop]["ms_total"] / ms_f, 4)},
+        "stages": stage_table(fstage, peak),
+        "roofline": kernel_roofline(fstage, ftop, peak, peak_src, ms_f, points_per_launch=min(fchunk, nloc)) if ftop else None,
+        "roofline_note": "the one-pass kernel moves 4*dim bytes per point plus the two grid-shaped fields: it is bound by "
+                         "instruction issue and the L1 / red paths, not by HBM (profiles/README.md); its HBM fraction "
+                         "is reported for completeness",
         "chain_roofline": {"note": "the reference formulation's minimal bytes per step (BASELINE.md section 3) "
                                    "over the fused step's time", "achieved": round(fchain_gbs, 1),
                            "peak": peak, "unit": "GB/s per GPU", "frac": round(fchain_gbs / peak, 4)},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample, repeats=2)
-    print(json.dumps(out), file=_OUT, flush=True)
+    if ms_j is not None:
+        out["fused"]["round1_jets_path"] = {"value": total / (ms_j * 1e-3), "unit": "points/s", "ms_per_step": ms_j,
+                                            "note": "jet.FusedPdeStep (jets -> tensor-core head -> scatter, 3 launches "
+                                                    "per chunk of %d points), 2 timed steps" % (4 * chunk)}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = {"rank": rank, "world": world, "local": local, "device": device}
+    out = measure_workload(args, args.workload, args.steps, args.warmup, ctx, with_jets=not args.no_extras)
+    # the 3D configuration rides along in the default single-GPU run (a driver-run record of config 4)
+    extra = None
+    if args.workload == "cfg5" and world == 1 and not args.no_extras and not args.points:
+        torch.cuda.empty_cache()
+        extra = measure_workload(args, "cfg4", max(2, min(args.steps, 5)), 3, ctx, with_jets=True)
+    if rank == 0:
+        if extra is not None:
+            for k in ("warmup", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "clocks", "index_mode", "n_gpus"):
+                extra.pop(k, None)
+            out["cfg4"] = extra
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample, repeats=2)
+        print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -502,8 +555,10 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": "%s: cells %s, %d points total, chunk %d, kernel %s, multicell, residual %s"
                                % (args.workload, list(shape), total, chunk, kernel, residual),
+                   "sample_points_per_step": sample,
                    "note": "reference CPU path = its pure-PyTorch sampler (test/grid_sampler.py, oracle "
-                           "port) under torch CPU autograd; bounded sample per step"},
+                           "port) under torch CPU autograd; each step is a bounded sample of %d points of the "
+                           "workload (points/s is size-normalised)" % sample},
         "cpu_baseline": desc,
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -533,6 +588,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2 ** 19,
                     help="points per CPU-baseline step (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the config-4 (3D) measurement and the round-1 jets path that ride along at N = 1")
     ap.add_argument("--nccl-reduce", action="store_true",
                     help="fused arm: reduce the gradients with NCCL instead of the peer-memory kernel")
     args = ap.parse_args()

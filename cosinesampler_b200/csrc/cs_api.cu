@@ -25,7 +25,7 @@ CS_DECLJ(launch_jet_d2_l0) CS_DECLJ(launch_jet_d2_l1) CS_DECLJ(launch_jet_d2_l2)
 CS_DECLJ(launch_jet_d3_l0) CS_DECLJ(launch_jet_d3_l1) CS_DECLJ(launch_jet_d3_l2) CS_DECLJ(launch_jet_d3_l3)
 #undef CS_DECLJ
 cudaError_t launch_head_any(int dim, int C, const HeadParams& p, cudaStream_t s);
-#define CS_DECLF(name) cudaError_t name(bool aggregate, FusedParams& p, cudaStream_t s);
+#define CS_DECLF(name) cudaError_t name(FusedParams& p, cudaStream_t s);
 CS_DECLF(launch_fused_d2_l0) CS_DECLF(launch_fused_d2_l1) CS_DECLF(launch_fused_d2_l2) CS_DECLF(launch_fused_d2_l3)
 CS_DECLF(launch_fused_d3_l0) CS_DECLF(launch_fused_d3_l1) CS_DECLF(launch_fused_d3_l2) CS_DECLF(launch_fused_d3_l3)
 #undef CS_DECLF
@@ -409,6 +409,16 @@ int bin_setup(const cs_problem* pb, cs::BinParams& b) {
             break;
         }
     }
+    // sub-texel bins (the cells of a multicell stack are offset by n/N of a texel: inside one sub-bin every
+    // cell sees the same corners): as fine as the point density allows, at least 4 points per sub-bin
+    if (b.shift == 0) {
+        const double density = (double)pb->P / ((double)pb->W * pb->H * pb->D);
+        while (b.sub < 2 && density >= 4.0 * (double)(1ll << (pb->dim * (b.sub + 1))) &&
+               ((long long)b.nbins << pb->dim) <= (1ll << 22)) {
+            b.sub += 1;
+            b.nbins <<= pb->dim;
+        }
+    }
     return 0;
 }
 
@@ -547,7 +557,8 @@ int cs_bin_workspace_bytes(const cs_problem* pb, int64_t* bytes) {
     cs::BinParams b;
     if (int rc = bin_setup(pb, b)) return rc;
     if (!bytes) return fail(CS_EINVAL, "cs_bin_workspace_bytes: bytes is NULL");
-    *bytes = round256((long long)b.nbins * 4) + round256((long long)pb->P * 4);
+    *bytes = round256((long long)b.nbins * 4) + round256(((long long)b.nbins / cs::BIN_SCAN_CHUNK + 1) * 4) +
+             round256((long long)pb->P * 4);
     return 0;
 }
 
@@ -559,22 +570,26 @@ int cs_bin_points(const cs_problem* pb, const float* coords, const float* offset
     if (!coords || !sorted || !workspace) return fail(CS_EINVAL, "cs_bin_points: NULL pointer");
     if (coords == sorted) return fail(CS_EINVAL, "cs_bin_points: sorted must not alias coords");
     const long long hist_bytes = round256((long long)b.nbins * 4);
-    if (workspace_bytes < hist_bytes + round256((long long)pb->P * 4))
+    const unsigned nchunks = (b.nbins + cs::BIN_SCAN_CHUNK - 1) / cs::BIN_SCAN_CHUNK;
+    const long long tot_bytes = round256(((long long)b.nbins / cs::BIN_SCAN_CHUNK + 1) * 4);
+    if (workspace_bytes < hist_bytes + tot_bytes + round256((long long)pb->P * 4))
         return fail(CS_EINVAL, "cs_bin_points: workspace too small (see cs_bin_workspace_bytes)");
     b.coords = coords; b.offset = offset;
     unsigned* hist = reinterpret_cast<unsigned*>(workspace);
-    unsigned* rank = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes);
+    unsigned* totals = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes);
+    unsigned* rank = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes + tot_bytes);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)b.nbins * 4, s);
     if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points memset");
     long long blocks = (pb->P + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     cs::cs_bin_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, rank);
-    cs::cs_bin_scan_kernel<<<1, 1024, 0, s>>>(hist, b.nbins);
-    cs::cs_bin_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, rank, sorted, perm);
+    cs::cs_bin_scan_chunk_kernel<<<nchunks, 1024, 0, s>>>(hist, b.nbins, totals);
+    cs::cs_bin_scan_totals_kernel<<<1, 1024, 0, s>>>(totals, nchunks);
+    cs::cs_bin_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, totals, rank, sorted, perm);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points launch");
-    g_launches.fetch_add(3, std::memory_order_relaxed);
+    g_launches.fetch_add(4, std::memory_order_relaxed);
     return 0;
 }
 
@@ -641,7 +656,7 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
     if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
     if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
     if (pb->index_mode < 0 || pb->index_mode > 1) return fail(CS_EINVAL, "bad index_mode %d", pb->index_mode);
-    if (aggregate < 0 || aggregate > 2) return fail(CS_EINVAL, "aggregate must be 0 (off), 1 (auto) or 2 (force)");
+    if (aggregate < 0 || aggregate > 1) return fail(CS_EINVAL, "aggregate must be 0 or 1");
     if (pb->N == 0 || pb->C == 0 || pb->P == 0) return 0;
     if (pb->field_layout != CS_LAYOUT_CHANNEL_LAST)
         return fail(CS_EUNSUPPORTED, "cs_pde_fused_step needs the channel-last mixed cells of cs_head_premix");
@@ -652,15 +667,14 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
         return fail(CS_EINVAL, "cs_pde_fused_step: NULL pointer");
     if (!aligned16(Vh) || !aligned16(gVh)) return fail(CS_EINVAL, "cs_pde_fused_step: Vh / gVh must be 16-byte aligned");
     const long long T = (long long)pb->D * pb->H * pb->W;
-    if (T * (long long)K >= (1ll << 31))
-        return fail(CS_EUNSUPPORTED, "a cell has %lld elements; the per-cell index is 32-bit", T * K);
+    if (((long long)pb->N * T + 1) * (long long)K >= (1ll << 31))
+        return fail(CS_EUNSUPPORTED, "the mixed cells have %lld elements; the texel index is 32-bit", ((long long)pb->N * T + 1) * K);
     if (pb->P >= (1ll << 33)) return fail(CS_EUNSUPPORTED, "too many points (%lld)", (long long)pb->P);
     cs::FusedParams p;
     memset(&p, 0, sizeof(p));
-    p.N = pb->N; p.K = K; p.P = pb->P;
+    p.N = pb->N; p.P = pb->P; p.T = T;
     p.size[0] = pb->W; p.size[1] = pb->H; p.size[2] = pb->D;
     p.tstride[0] = 1; p.tstride[1] = pb->W; p.tstride[2] = pb->W * pb->H;
-    p.cell_stride = T * K;
     p.Vh = Vh; p.gVh = gVh; p.coords = coords; p.offset = offset;
     p.b1 = b1; p.w2 = w2; p.b2 = b2;
     p.gb1 = gb1; p.gw2 = gw2; p.gb2 = gb2; p.loss_sum = loss_sum;
@@ -672,21 +686,12 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
     p.multicell = pb->multicell; p.index_mode = pb->index_mode;
     const int v = K / 4;
     const int lshift = (v == 1) ? 0 : (v == 2) ? 1 : (v == 4) ? 2 : 3;
-    // aggregation windows: 2D only, and only while 3 warps' worth of them leave room for 2 blocks per SM
-    bool agg = false;
-    if (aggregate && pb->dim == 2) {
-        const int L = 1 << lshift, NW = 32 >> lshift;
-        const long long per_warp = (long long)(3 * 4 * NW + NW * (cs::fused_win_stride(pb->N, L) + pb->N)) * 16;
-        agg = 3 * per_warp <= 110 * 1024;
-        if (!agg && aggregate == 2) return fail(CS_EUNSUPPORTED, "aggregation windows of %d cells do not fit in shared memory", pb->N);
-    } else if (aggregate == 2) {
-        return fail(CS_EUNSUPPORTED, "aggregation windows are implemented for dim == 2");
-    }
-    using Fn = cudaError_t (*)(bool, cs::FusedParams&, cudaStream_t);
+    p.aggregate = aggregate ? 1 : 0;
+    using Fn = cudaError_t (*)(cs::FusedParams&, cudaStream_t);
     static const Fn table[2][4] = {
         {cs::launch_fused_d2_l0, cs::launch_fused_d2_l1, cs::launch_fused_d2_l2, cs::launch_fused_d2_l3},
         {cs::launch_fused_d3_l0, cs::launch_fused_d3_l1, cs::launch_fused_d3_l2, cs::launch_fused_d3_l3}};
-    cudaError_t e = table[pb->dim - 2][lshift](agg, p, (cudaStream_t)stream);
+    cudaError_t e = table[pb->dim - 2][lshift](p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "fused step kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;

@@ -20,16 +20,16 @@
 //     the step is the coordinates (4*dim bytes).
 //  2. Loss and gradients do not depend on the order of the points, so the step may bin them by texel first
 //     (cs_bin_points: counting sort on a tile-major texel key).  Consecutive points then hit the same corners.
-//  3. With binned points the scatter pre-reduces before it touches L2: every *walker* (the L = K/4 lanes that
-//     share a point) owns a contiguous range of the binned points and keeps, per cell, a private 3x3-texel
-//     window of the accumulator in shared memory (the N cells of a point differ by the sub-texel multicell
-//     offset, so their corners lie within one texel of each other: 3x3 covers every cell's 2x2 corners).
-//     Contributions are added with plain ld/st.shared (the window is private: no atomics), and a window is
-//     flushed with one red.global.add.v4.f32 per touched texel when the walker moves to the next texel.  At
-//     16-65 points per texel that is 7-28x fewer reds than one per (point, corner).
-//     (Warp-level __match_any_sync aggregation was the alternative: it needs the points of a warp to agree in
-//     corner AND sub-texel shift, and a 3-step segmented shuffle per contribution; ATOMS-based privatisation
-//     costs 2 cycles per lane.  Private windows need neither.)
+//  3. With binned points the scatter pre-reduces before it touches L2: the points are binned on a key that
+//     also holds the sub-texel quadrant (for N cells offset by n/N of a texel, every cell's corners are the same
+//     for all points of one sub-bin), each walker (the L = K/4 lanes that share a point) takes consecutive
+//     binned points, and contributions of consecutive points with identical corners are summed in registers
+//     and leave as ONE red.global.add.v4.f32 per corner and run instead of one per corner and point.
+//     Measured alternatives (profiles/README.md): walker-private 3x3-texel windows in shared memory (plain
+//     ld/st.shared read-modify-write, flushed when the walker moves on) cut the reds 7-28x but cost 22 KB of
+//     shared memory per warp (6 warps per SM) and a serial LDS->FADD->STS chain per corner: 1.29 ms per 2^20
+//     points against 0.53 ms without; ATOMS-based privatisation costs 2 cycles per lane; __match_any_sync
+//     needs the points of a warp to agree in corner AND sub-texel shift plus a segmented shuffle per value.
 #pragma once
 #include <limits.h>
 
@@ -38,12 +38,13 @@
 namespace cs {
 
 // ---------------------------------------------------------------------------------------------------------
-// Point binning: counting sort of the coordinates on a tile-major texel key
+// Point binning: counting sort of the coordinates on a tile-major texel key (+ sub-texel quadrant)
 // ---------------------------------------------------------------------------------------------------------
 struct BinParams {
     int dim;
     int size[3];
     int shift;                 // texel coordinates are coarsened by >> shift so that nbins stays bounded
+    int sub;                   // log2 of the sub-bins per texel and axis (0, 1, 2)
     int ntx, nty, ntz;         // tiles per axis (2D: 8x8 texels, 3D: 4x4x4 texels per tile)
     unsigned nbins;
     long long P;
@@ -51,10 +52,11 @@ struct BinParams {
     const float* offset;       // [N] (device); cell 0's offset enters the key.  nullable = 0
     int align, multicell, index_mode;
 };
+constexpr int BIN_SCAN_CHUNK = 2048;   // bins per block of the two-level scan
 
-// low-corner texel of cell 0 along one axis, clamped into the cell: a locality key, never a correctness
-// matter (the fused kernel compares the real corner indices of every point)
-__device__ __forceinline__ int bin_axis(float g, int size, float off0, const BinParams& p) {
+// low-corner texel of cell 0 along one axis, clamped into the cell, and the sub-bin of the fractional position:
+// a locality key, never a correctness matter (the fused kernel compares the real corner indices of every point)
+__device__ __forceinline__ int bin_axis(float g, int size, float off0, const BinParams& p, int& subbin) {
     float i;
     if (p.align) {
         const float sf = (float)(size - 1 - (p.multicell ? 1 : 0));
@@ -65,26 +67,33 @@ __device__ __forceinline__ int bin_axis(float g, int size, float off0, const Bin
         i = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), sf), -1.f), 0.5f), off0);
     }
     if (!(fabsf(i) < 1.0e9f)) i = 0.f;
-    int l = (int)floorf(i);
-    l = max(0, min(size - 1, l));
+    const float lf = floorf(i);
+    int l = (int)lf;
+    subbin = min((1 << p.sub) - 1, max(0, (int)((i - lf) * (float)(1 << p.sub))));
+    if (l < 0) { l = 0; subbin = 0; }
+    if (l > size - 1) { l = size - 1; subbin = 0; }
     return l >> p.shift;
 }
 
 __device__ __forceinline__ unsigned bin_key(const float* gp, const BinParams& p) {
     const float off0 = p.offset ? __ldg(p.offset) : 0.f;
-    const int lx = bin_axis(__ldg(gp), p.size[0], off0, p);
-    const int ly = bin_axis(__ldg(gp + 1), p.size[1], off0, p);
+    int sx, sy, sz = 0;
+    const int lx = bin_axis(__ldg(gp), p.size[0], off0, p, sx);
+    const int ly = bin_axis(__ldg(gp + 1), p.size[1], off0, p, sy);
+    unsigned key;
     if (p.dim == 2) {
         const unsigned tile = (unsigned)((ly >> 3) * p.ntx + (lx >> 3));
-        return (tile << 6) | (unsigned)(((ly & 7) << 3) | (lx & 7));
+        key = (tile << 6) | (unsigned)(((ly & 7) << 3) | (lx & 7));
+        return (key << (2 * p.sub)) | (unsigned)((sy << p.sub) | sx);
     }
-    const int lz = bin_axis(__ldg(gp + 2), p.size[2], off0, p);
+    const int lz = bin_axis(__ldg(gp + 2), p.size[2], off0, p, sz);
     const unsigned tile = (unsigned)(((lz >> 2) * p.nty + (ly >> 2)) * p.ntx + (lx >> 2));
-    return (tile << 6) | (unsigned)(((lz & 3) << 4) | ((ly & 3) << 2) | (lx & 3));
+    key = (tile << 6) | (unsigned)(((lz & 3) << 4) | ((ly & 3) << 2) | (lx & 3));
+    return (key << (3 * p.sub)) | (unsigned)((((sz << p.sub) | sy) << p.sub) | sx);
 }
 
 static __global__ void __launch_bounds__(256) cs_bin_count_kernel(const BinParams p, unsigned* __restrict__ hist,
-                                                           unsigned* __restrict__ rank) {
+                                                                  unsigned* __restrict__ rank) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P;
          i += (long long)gridDim.x * blockDim.x) {
         const unsigned key = bin_key(p.coords + i * p.dim, p);
@@ -92,39 +101,61 @@ static __global__ void __launch_bounds__(256) cs_bin_count_kernel(const BinParam
     }
 }
 
-// exclusive scan of hist[0..nbins) in place, one block
-static __global__ void __launch_bounds__(1024) cs_bin_scan_kernel(unsigned* __restrict__ hist, unsigned nbins) {
+// two-level exclusive scan: every block scans BIN_SCAN_CHUNK bins in place and writes its total; one block
+// scans the totals; the scatter adds both
+static __global__ void __launch_bounds__(1024) cs_bin_scan_chunk_kernel(unsigned* __restrict__ hist, unsigned nbins,
+                                                                        unsigned* __restrict__ totals) {
     __shared__ unsigned part[1024];
-    const unsigned per = (nbins + 1023u) / 1024u;
-    const unsigned b0 = threadIdx.x * per;
-    const unsigned b1 = min(nbins, b0 + per);
-    unsigned s = 0;
-    for (unsigned b = b0; b < b1; ++b) s += hist[b];
+    const unsigned b0 = blockIdx.x * BIN_SCAN_CHUNK + 2 * threadIdx.x;
+    const unsigned c0 = b0 < nbins ? hist[b0] : 0u;
+    const unsigned c1 = b0 + 1 < nbins ? hist[b0 + 1] : 0u;
+    const unsigned s = c0 + c1;
     part[threadIdx.x] = s;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partial sums
     for (int o = 1; o < 1024; o <<= 1) {
-        unsigned v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
+        const unsigned v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned excl = part[threadIdx.x] - s;
+    if (b0 < nbins) hist[b0] = excl;
+    if (b0 + 1 < nbins) hist[b0 + 1] = excl + c0;
+    if (threadIdx.x == 1023) totals[blockIdx.x] = part[1023];
+}
+
+static __global__ void __launch_bounds__(1024) cs_bin_scan_totals_kernel(unsigned* __restrict__ totals, unsigned n) {
+    __shared__ unsigned part[1024];
+    const unsigned per = (n + 1023u) / 1024u;
+    const unsigned b0 = threadIdx.x * per;
+    const unsigned b1 = min(n, b0 + per);
+    unsigned s = 0;
+    for (unsigned b = b0; b < b1; ++b) s += totals[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
         __syncthreads();
         part[threadIdx.x] += v;
         __syncthreads();
     }
     unsigned run = part[threadIdx.x] - s;
     for (unsigned b = b0; b < b1; ++b) {
-        const unsigned c = hist[b];
-        hist[b] = run;
+        const unsigned c = totals[b];
+        totals[b] = run;
         run += c;
     }
 }
 
 static __global__ void __launch_bounds__(256) cs_bin_scatter_kernel(const BinParams p, const unsigned* __restrict__ offs,
-                                                             const unsigned* __restrict__ rank,
-                                                             float* __restrict__ sorted, int* __restrict__ perm) {
+                                                                    const unsigned* __restrict__ totals,
+                                                                    const unsigned* __restrict__ rank,
+                                                                    float* __restrict__ sorted, int* __restrict__ perm) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P;
          i += (long long)gridDim.x * blockDim.x) {
         const float* gp = p.coords + i * p.dim;
         const unsigned key = bin_key(gp, p);
-        const long long pos = (long long)__ldg(offs + key) + __ldg(rank + i);
+        const long long pos = (long long)__ldg(offs + key) + __ldg(totals + key / BIN_SCAN_CHUNK) + __ldg(rank + i);
         float* dst = sorted + pos * p.dim;
         for (int a = 0; a < p.dim; ++a) dst[a] = __ldg(gp + a);
         if (perm) perm[pos] = (int)i;
@@ -137,13 +168,14 @@ static __global__ void __launch_bounds__(256) cs_bin_scatter_kernel(const BinPar
 constexpr int MIX_MAXK = 32;
 
 // Vh[n, t, k] = sum_c W1[k, c] * V[n, c, t]   (channel-first in, channel-last out: the staging transpose of
-// cs_to_channel_last and the first Linear layer in one pass)
+// cs_to_channel_last and the first Linear layer in one pass); Vh[N*T, :] = 0 (the texel out-of-bounds corners read)
 template <int K>
 __global__ void __launch_bounds__(256) cs_head_premix_kernel(const float* __restrict__ V, const float* __restrict__ W1,
                                                              float* __restrict__ Vh, int C, long long T, long long NT) {
     extern __shared__ float w1s[];           // [C][K]: w1s[c*K + k] = W1[k*C + c]
     for (int e = threadIdx.x; e < K * C; e += blockDim.x) w1s[(e % C) * K + (e / C)] = __ldg(W1 + e);
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < K) Vh[NT * K + threadIdx.x] = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NT;
          i += (long long)gridDim.x * blockDim.x) {
         const long long n = i / T, t = i - n * T;
@@ -258,13 +290,13 @@ __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float
 // The fused step
 // ---------------------------------------------------------------------------------------------------------
 struct FusedParams {
-    int N, K;                 // cells, hidden width = channels of Vh / gVh
+    int N;                    // cells
     int size[3];
     int tstride[3];
+    long long T;              // texels per cell
     long long P;
-    long long cell_stride;    // T * K
-    const float* Vh;          // [N, T, K]  W1-mixed cells (cs_head_premix)
-    float* gVh;               // [N, T, K]  accumulated
+    const float* Vh;          // [N*T + 1, K]  W1-mixed cells (cs_head_premix); the extra texel is zero
+    float* gVh;               // [N*T + 1, K]  accumulated; the extra texel absorbs out-of-bounds corners
     const float* coords;      // [P, DIM]   (binned: cs_bin_points)
     const float* offset;      // [N]
     const float* b1;          // [K]
@@ -278,47 +310,62 @@ struct FusedParams {
     float scale;
     int cvec2;
     int pad, align, kernel, multicell, index_mode;
-    long long pts_per_walker; // AGG: contiguous points per walker (a multiple of PPQ)
-    long long num_ptiles;     // !AGG: warp tiles of PTS consecutive points
-    int win_stride;           // AGG: float4 per walker window (N*9*L padded)
+    int aggregate;            // pre-reduce the scatter over runs of points that share their corners
+    long long num_ptiles;     // warp tiles of PTS consecutive points
+    long long tiles_per_warp; // each warp walks a contiguous range of tiles (binned points: cache reuse)
 };
 
-// Phase 1 for one (cell, point): field 0 = (base texel, corner-valid mask, low corner x, low corner y) as int
-// bits, field 1 + a = (w0, w1, m k', m^2 k'') of axis a.
+// Phase 1 for one (cell, point).  Record fields (float4 each, [field][point]):
+//   0 .. CQ-1 : texel index of each of the 2^DIM corners relative to this cell's first texel (int bits, corner c
+//               = bit a set -> high corner along axis a); a corner outside the cell points at the extra texel
+//               behind the last cell (zero in Vh, a dump in gVh): gathers and reds need no predicate
+//   CQ + a    : (w1, m k', -m^2 k'', w0) of axis a: weight of the high corner, d weight / d coordinate of the
+//               high corner, d2 weight / d coordinate^2 of the high corner (opposite signs for the low corner)
 template <int DIM, int PTS>
 __device__ __forceinline__ void build_fused_record(float4* rec4, int i, const float (&g)[DIM], bool in_range,
-                                                   float off, const FusedParams& p) {
-    int base = 0, mask = 0, l0 = 0, l1 = 0;
+                                                   float off, int pad_index, const FusedParams& p) {
+    constexpr int NCORN = 1 << DIM;
+    constexpr int CQ = NCORN / 4;
+    int idx[NCORN];
     float4 ax[DIM];
 #pragma unroll
     for (int a = 0; a < DIM; ++a) ax[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NCORN; ++c) idx[c] = pad_index;
     if (in_range) {
         bool ok = true;
         bool lo_ok[DIM], hi_ok[DIM];
+        int base = 0;
 #pragma unroll
         for (int a = 0; a < DIM; ++a) {
             const AxisRec ar = axis_setup(g[a], p.size[a], off, p, p.align != 0, 2);
             ok = ok && ar.ok;
             base += ar.l * p.tstride[a];
-            if (a == 0) l0 = ar.l;
-            if (a == 1) l1 = ar.l;
             lo_ok[a] = (ar.l >= 0) && (ar.l < p.size[a]);
             hi_ok[a] = (ar.l + 1 >= 0) && (ar.l + 1 < p.size[a]);
-            ax[a] = make_float4(ar.w0, ar.w1, ar.d, ar.e);
+            ax[a] = make_float4(ar.w1, ar.d, -ar.e, ar.w0);
         }
         if (ok) {
 #pragma unroll
-            for (int c = 0; c < (1 << DIM); ++c) {
+            for (int c = 0; c < NCORN; ++c) {
                 bool valid = true;
+                int o = base;
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) valid = valid && (((c >> a) & 1) ? hi_ok[a] : lo_ok[a]);
-                if (valid) mask |= 1 << c;
+                for (int a = 0; a < DIM; ++a) {
+                    const bool hi = (c >> a) & 1;
+                    valid = valid && (hi ? hi_ok[a] : lo_ok[a]);
+                    o += hi ? p.tstride[a] : 0;
+                }
+                if (valid) idx[c] = o;
             }
         }
     }
-    rec4[i] = make_float4(__int_as_float(base), __int_as_float(mask), __int_as_float(l0), __int_as_float(l1));
 #pragma unroll
-    for (int a = 0; a < DIM; ++a) rec4[(1 + a) * PTS + i] = ax[a];
+    for (int h = 0; h < CQ; ++h)
+        rec4[h * PTS + i] = make_float4(__int_as_float(idx[4 * h]), __int_as_float(idx[4 * h + 1]),
+                                        __int_as_float(idx[4 * h + 2]), __int_as_float(idx[4 * h + 3]));
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) rec4[(CQ + a) * PTS + i] = ax[a];
 }
 
 __device__ __forceinline__ float tanh_ex2(float x) {
@@ -330,46 +377,42 @@ __device__ __forceinline__ float tanh_ex2(float x) {
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// flush one (walker, cell) window: one red.global.add.v4.f32 per touched, in-bounds texel; the window is
-// zeroed again.  Called by the walkers that move on while the others idle (warp-divergent by design).
-static __device__ __noinline__ void flush_window(float4* w, int L, int touched, int ox, int oy, float* gcell, int K,
-                                          int W, int H) {
-#pragma unroll 1
-    for (int s = 0; s < 9; ++s) {
-        if ((touched >> s) & 1) {
-            const float4 v = w[s * L];
-            w[s * L] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int x = ox + (s % 3), y = oy + (s / 3);
-            if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
-                red_add_v4(gcell + ((long long)y * W + x) * K, v.x, v.y, v.z, v.w);
-        }
-    }
+// One channel of one (x, y) slab: bilinear-type blend with the high-corner weights w1x, w1y (w0 = 1 - w1 for
+// all three kernels).  A = value, T = d/dx / (m k'x) = d2/dx2 / (-m^2 k''x), DA = d/dy / (m k'y).
+struct SlabOut { float A, T, DA; };
+__device__ __forceinline__ SlabOut slab_blend(float v00, float v10, float v01, float v11, float w1x, float w1y) {
+    const float d0 = v10 - v00, d1 = v11 - v01;
+    const float a0 = fmaf(d0, w1x, v00), a1 = fmaf(d1, w1x, v01);
+    SlabOut o;
+    o.DA = a1 - a0;
+    o.A = fmaf(o.DA, w1y, a0);
+    o.T = fmaf(d1 - d0, w1y, d0);
+    return o;
 }
 
-// register budget: 9 warps per SM (3 blocks of 96 threads, the shared-memory limit of the aggregating variant
-// at N = 4 cells) leave 227 registers per thread
-#ifndef CS_FUSED_MAXREG_AGG
-#define CS_FUSED_MAXREG_AGG 224
+#ifndef CS_FUSED_BLOCKS
+#define CS_FUSED_BLOCKS 3
 #endif
-#ifndef CS_FUSED_MAXREG
-#define CS_FUSED_MAXREG 224
-#endif
-constexpr int FUSED_THREADS_AGG = 96;
-constexpr int FUSED_THREADS = 96;
+constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_MAX_CELLS = 32;      // the records of all cells of a tile live in shared memory
 
-template <int DIM, int LSHIFT, bool AGG>
-__global__ void __maxnreg__(AGG ? CS_FUSED_MAXREG_AGG : CS_FUSED_MAXREG)
+// Code size matters here: three inlined phases unrolled over the points of a walker were 8000 SASS
+// instructions (128 KB) and the kernel stalled on instruction fetch.  Gather + head run one point at a time in
+// a real loop (the finished point is rotated into the register tile), phase 1 has one call site, and corners
+// need no validity predicates: ~1500 instructions.
+template <int DIM, int LSHIFT>
+__global__ void __launch_bounds__(FUSED_THREADS, CS_FUSED_BLOCKS)
 cs_pde_fused_kernel(const FusedParams p) {
     constexpr int NCORN = 1 << DIM;
+    constexpr int CQ = NCORN / 4;
     constexpr int J = 1 + 2 * DIM;
     constexpr int L = 1 << LSHIFT;
-    constexpr int NW = 32 >> LSHIFT;                 // walkers per warp
-    constexpr int PPQ = (DIM == 2) ? 4 : 2;          // points per walker and iteration
-    constexpr int PTS = PPQ * NW;                    // points per warp and iteration
+    constexpr int K = 4 * L;                         // hidden width: 4 units per lane, L lanes per point
+    constexpr int NW = 32 >> LSHIFT;                 // walkers (point slots) per warp
+    constexpr int PPQ = (DIM == 2) ? 4 : 2;          // consecutive points per walker and tile
+    constexpr int PTS = PPQ * NW;                    // points per warp tile
     constexpr int PPL = (PTS + 31) / 32;
-    constexpr int REC1 = (1 + DIM) * PTS;            // float4 per record buffer
-    constexpr int FULL = (1 << NCORN) - 1;
-    static_assert(!AGG || DIM == 2, "aggregation windows are two-dimensional");
+    constexpr int REC1 = (CQ + DIM) * PTS;           // float4 per record buffer (one cell)
 
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31;
@@ -378,26 +421,8 @@ cs_pde_fused_kernel(const FusedParams p) {
     const int q = lane >> LSHIFT;
     const int j = lane & (L - 1);
     const int ncells = p.N;
-    const int K = p.K;
-    const int per_warp = REC1 + (AGG ? NW * p.win_stride + NW * ncells : 0);
-    float4* rec = smem4 + (size_t)warp * per_warp;
-    float4* win = rec + REC1 + (AGG ? q * p.win_stride + j : 0);               // this lane's column of its walker's windows
-    int4* hdr = reinterpret_cast<int4*>(rec + REC1 + (AGG ? NW * p.win_stride : 0)) + (AGG ? q * ncells : 0);
+    float4* recw = smem4 + (size_t)warp * ncells * REC1;
 
-    if (AGG) {
-        for (int s = 0; s < ncells * 9; ++s) win[s * L] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j == 0)
-            for (int n = 0; n < ncells; ++n) hdr[n] = make_int4(INT_MIN, INT_MIN, 0, 0);
-        __syncwarp();
-    }
-
-    int coff[NCORN];
-#pragma unroll
-    for (int c = 0; c < NCORN; ++c) {
-        coff[c] = 0;
-#pragma unroll
-        for (int a = 0; a < DIM; ++a) coff[c] += ((c >> a) & 1) * p.tstride[a];
-    }
     float b1k[4], w2k[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { b1k[k] = __ldg(p.b1 + 4 * j + k); w2k[k] = __ldg(p.w2 + 4 * j + k); }
@@ -406,20 +431,15 @@ cs_pde_fused_kernel(const FusedParams p) {
     float gb2acc = 0.f, lossacc = 0.f;
 
     const long long gw = (long long)blockIdx.x * wpb + warp;
-    const long long tw = (long long)gridDim.x * wpb;
-    const long long R = p.pts_per_walker;
-    // first point of (walker qq, iteration it)
-    auto first_point = [&](int qq, long long it) -> long long {
-        return AGG ? (gw * NW + qq) * R + it * PPQ : (gw + it * tw) * PTS + (long long)qq * PPQ;
-    };
-    auto iteration_live = [&](long long it) -> bool {
-        return AGG ? (it * PPQ < R && first_point(0, it) < p.P) : (gw + it * tw < p.num_ptiles);
-    };
-    auto load_coords = [&](float (&g)[PPL][DIM], bool (&inr)[PPL], long long it) {
+    const long long tile_begin = gw * p.tiles_per_warp;
+    long long tile_end = tile_begin + p.tiles_per_warp;
+    if (tile_end > p.num_ptiles) tile_end = p.num_ptiles;
+
+    auto load_coords = [&](float (&g)[PPL][DIM], bool (&inr)[PPL], long long tile) {
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
             const int i = u * 32 + lane;
-            const long long pi = first_point(i / PPQ, it) + (i % PPQ);
+            const long long pi = tile * PTS + i;
             inr[u] = (i < PTS) && (pi < p.P);
 #pragma unroll
             for (int a = 0; a < DIM; ++a) g[u][a] = 0.f;
@@ -435,31 +455,32 @@ cs_pde_fused_kernel(const FusedParams p) {
             }
         }
     };
-    // records of cell n for the PTS points of this iteration; returns "every corner of every point is valid"
-    auto phase1 = [&](const float (&g)[PPL][DIM], const bool (&inr)[PPL], int n) -> bool {
-        const float off = __ldg(p.offset + n);
-        __syncwarp();                               // everyone is done reading the record buffer
-        bool allv = true;
-#pragma unroll
-        for (int u = 0; u < PPL; ++u) {
-            const int i = u * 32 + lane;
-            if (i < PTS) {
-                build_fused_record<DIM, PTS>(rec, i, g[u], inr[u], off, p);
-                allv = allv && (__float_as_int(rec[i].y) == FULL);
-            }
-        }
-        return __all_sync(0xffffffffu, allv);       // also a warp barrier: records are visible
-    };
 
     float gcur[PPL][DIM], gnext[PPL][DIM];
     bool icur[PPL], inext[PPL];
-    if (iteration_live(0)) {
-    load_coords(gcur, icur, 0);
-    for (long long it = 0;; ++it) {
-        const bool have_next = iteration_live(it + 1);
-        if (have_next) load_coords(gnext, inext, it + 1);
+    if (tile_begin < tile_end) load_coords(gcur, icur, tile_begin);
 
-        // ---- A: gather.  acc[jt][t][k] = H_jt of point t, hidden unit 4j + k, summed over the cells
+#pragma unroll 1
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+        const bool have_next = tile + 1 < tile_end;
+        if (have_next) load_coords(gnext, inext, tile + 1);
+        const long long qp0 = tile * PTS + (long long)q * PPQ;      // first point of this walker
+
+        // ---- phase 1: records of every cell for the PTS points of this tile, one point per lane
+        __syncwarp();                                   // everyone is done reading the previous tile's records
+#pragma unroll 1
+        for (int n = 0; n < ncells; ++n) {
+            const float off = __ldg(p.offset + n);
+            const int pad_index = (int)((long long)(ncells - n) * p.T);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+                const int i = u * 32 + lane;
+                if (i < PTS) build_fused_record<DIM, PTS>(recw + n * REC1, i, gcur[u], icur[u], off, pad_index, p);
+            }
+        }
+        __syncwarp();                                   // records are visible
+
+        // acc[jt][t][k] = d loss / d H_jt of point t of this walker, hidden unit 4j + k
         float acc[J][PPQ][4];
 #pragma unroll
         for (int jt = 0; jt < J; ++jt)
@@ -467,76 +488,82 @@ cs_pde_fused_kernel(const FusedParams p) {
             for (int t = 0; t < PPQ; ++t)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[jt][t][k] = 0.f;
-        for (int n = 0; n < ncells; ++n) {
-            const bool allv = phase1(gcur, icur, n);
-            const float* vsrc = p.Vh + (long long)n * p.cell_stride + 4 * j;
-            float4 v[PPQ][NCORN];
+
+        // ---- A + B, one point at a time
+#pragma unroll 1
+        for (int t = 0; t < PPQ; ++t) {
+            const int ri = PPQ * q + t;
+            // A: gather.  h[jt][k] = H_jt of this point, hidden unit 4j + k, summed over the cells
+            float h[J][4];
 #pragma unroll
-            for (int t = 0; t < PPQ; ++t) {
-                const float4 hd = rec[PPQ * q + t];
-                const int base = __float_as_int(hd.x);
-                const int mask = __float_as_int(hd.y);
+            for (int jt = 0; jt < J; ++jt)
 #pragma unroll
-                for (int c = 0; c < NCORN; ++c) {
-                    if (allv) v[t][c] = ldg_f4(vsrc + (long long)(base + coff[c]) * K);
-                    else v[t][c] = ((mask >> c) & 1) ? ldg_f4(vsrc + (long long)(base + coff[c]) * K)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) h[jt][k] = 0.f;
+#pragma unroll 2
+            for (int n = 0; n < ncells; ++n) {
+                const float4* rec = recw + n * REC1;
+                const float* vsrc = p.Vh + (long long)n * p.T * K + 4 * j;
+                float4 v[NCORN];
+#pragma unroll
+                for (int hq = 0; hq < CQ; ++hq) {
+                    const float4 ix = rec[hq * PTS + ri];
+                    v[4 * hq + 0] = ldg_f4(vsrc + (long long)__float_as_int(ix.x) * K);
+                    v[4 * hq + 1] = ldg_f4(vsrc + (long long)__float_as_int(ix.y) * K);
+                    v[4 * hq + 2] = ldg_f4(vsrc + (long long)__float_as_int(ix.z) * K);
+                    v[4 * hq + 3] = ldg_f4(vsrc + (long long)__float_as_int(ix.w) * K);
                 }
-            }
-#pragma unroll
-            for (int t = 0; t < PPQ; ++t) {
-                const int ri = PPQ * q + t;
-                const float4 ax = rec[1 * PTS + ri];
-                const float4 ay = rec[2 * PTS + ri];
+                const float4 ax = rec[CQ * PTS + ri];            // (w1, d, -e, w0)
+                const float4 ay = rec[(CQ + 1) * PTS + ri];
                 if (DIM == 2) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const SlabJet sj = slab_contract(f4get(v[t][0], k), f4get(v[t][1], k), f4get(v[t][2], k),
-                                                         f4get(v[t][3], k), ax, ay);
-                        acc[0][t][k] += sj.A;
-                        acc[1][t][k] += sj.X;
-                        acc[2][t][k] += sj.Y;
-                        acc[3][t][k] += sj.XX;
-                        acc[4][t][k] += sj.YY;
+                        const SlabOut o = slab_blend(f4get(v[0], k), f4get(v[1], k), f4get(v[2], k), f4get(v[3], k), ax.x, ay.x);
+                        h[0][k] += o.A;
+                        h[1][k] = fmaf(ax.y, o.T, h[1][k]);
+                        h[2][k] = fmaf(ay.y, o.DA, h[2][k]);
+                        h[3][k] = fmaf(ax.z, o.T, h[3][k]);
+                        h[4][k] = fmaf(ay.z, o.DA, h[4][k]);
                     }
                 } else {
-                    const float4 az = rec[(DIM == 3 ? 3 : 2) * PTS + ri];
+                    const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTS + ri];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const SlabJet lo = slab_contract(f4get(v[t][0], k), f4get(v[t][1], k), f4get(v[t][2], k),
-                                                         f4get(v[t][3], k), ax, ay);
-                        const SlabJet hi = slab_contract(f4get(v[t][4 % NCORN], k), f4get(v[t][5 % NCORN], k),
-                                                         f4get(v[t][6 % NCORN], k), f4get(v[t][7 % NCORN], k), ax, ay);
-                        acc[0][t][k] += fmaf(hi.A, az.y, lo.A * az.x);
-                        acc[1][t][k] += fmaf(hi.X, az.y, lo.X * az.x);
-                        acc[2][t][k] += fmaf(hi.Y, az.y, lo.Y * az.x);
-                        acc[DIM][t][k] += (hi.A - lo.A) * az.z;
-                        acc[1 + DIM][t][k] += fmaf(hi.XX, az.y, lo.XX * az.x);
-                        acc[(2 + DIM) % J][t][k] += fmaf(hi.YY, az.y, lo.YY * az.x);
-                        acc[2 * DIM][t][k] += (lo.A - hi.A) * az.w;
+                        const SlabOut lo = slab_blend(f4get(v[0], k), f4get(v[1], k), f4get(v[2], k), f4get(v[3], k), ax.x, ay.x);
+                        const SlabOut hi = slab_blend(f4get(v[4 % NCORN], k), f4get(v[5 % NCORN], k), f4get(v[6 % NCORN], k),
+                                                      f4get(v[7 % NCORN], k), ax.x, ay.x);
+                        const float dA = hi.A - lo.A;
+                        const float tz = fmaf(hi.T - lo.T, az.x, lo.T);
+                        const float daz = fmaf(hi.DA - lo.DA, az.x, lo.DA);
+                        h[0][k] += fmaf(dA, az.x, lo.A);
+                        h[1][k] = fmaf(ax.y, tz, h[1][k]);
+                        h[2][k] = fmaf(ay.y, daz, h[2][k]);
+                        h[DIM][k] = fmaf(az.y, dA, h[DIM][k]);
+                        h[1 + DIM][k] = fmaf(ax.z, tz, h[1 + DIM][k]);
+                        h[(2 + DIM) % J][k] = fmaf(ay.z, daz, h[(2 + DIM) % J][k]);
+                        h[2 * DIM][k] = fmaf(az.z, dA, h[2 * DIM][k]);
                     }
                 }
             }
-        }
 
-        // ---- B: head + residual + loss, and d loss / d H_jt in place (test_2d.py:42-127 in closed form)
-#pragma unroll
-        for (int t = 0; t < PPQ; ++t) {
-            float th[4], s1[4], s2[4];
+            // B: head + residual + loss, and d loss / d H_jt in place (test_2d.py:42-127 in closed form):
+            //   t = tanh h, s1 = 1 - t^2, s2 = -2 t s1, s3 = -2 (s1^2 + t s2)
+            //   u = w2.t + b2, u_a = w2.(s1 hd_a), u_aa = w2.(s2 hd_a^2 + s1 hdd_a)
+            float th[4], ws1[4], ws2[4];
             float pu = 0.f, pua[DIM], puaa[DIM];
 #pragma unroll
             for (int a = 0; a < DIM; ++a) { pua[a] = 0.f; puaa[a] = 0.f; }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                th[k] = tanh_ex2(acc[0][t][k] + b1k[k]);
-                s1[k] = 1.f - th[k] * th[k];
-                s2[k] = -2.f * th[k] * s1[k];
+                th[k] = tanh_ex2(h[0][k] + b1k[k]);
+                const float s1 = fmaf(-th[k], th[k], 1.f);
+                ws1[k] = w2k[k] * s1;                            // w2 s1
+                ws2[k] = -2.f * th[k] * ws1[k];                  // w2 s2
                 pu = fmaf(w2k[k], th[k], pu);
 #pragma unroll
                 for (int a = 0; a < DIM; ++a) {
-                    const float hd = acc[1 + a][t][k], hdd = acc[1 + DIM + a][t][k];
-                    pua[a] = fmaf(w2k[k], s1[k] * hd, pua[a]);
-                    puaa[a] = fmaf(w2k[k], s2[k] * hd * hd + s1[k] * hdd, puaa[a]);
+                    const float hd = h[1 + a][k];
+                    pua[a] = fmaf(ws1[k], hd, pua[a]);
+                    puaa[a] = fmaf(ws2[k], hd * hd, fmaf(ws1[k], h[1 + DIM + a][k], puaa[a]));
                 }
             }
 #pragma unroll
@@ -552,7 +579,7 @@ cs_pde_fused_kernel(const FusedParams p) {
             float f = p.c_u * u + p.c_u3 * u * u * u;
 #pragma unroll
             for (int a = 0; a < DIM; ++a) f += p.c1[a] * pua[a] + p.c2[a] * puaa[a];
-            const bool valid = first_point(q, it) + t < p.P;
+            const bool valid = qp0 + t < p.P;
             const float gg = valid ? 2.f * p.scale * f : 0.f;
             const float gsc = gg * (p.c_u + 3.f * p.c_u3 * u * u);
             if (j == 0) {
@@ -564,139 +591,129 @@ cs_pde_fused_kernel(const FusedParams p) {
             for (int a = 0; a < DIM; ++a) { g1c[a] = gg * p.c1[a]; g2c[a] = gg * p.c2[a]; }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float d1 = s1[k], d2 = s2[k];
-                const float d3 = -2.f * (d1 * d1 + th[k] * d2);
-                float gw2 = gsc * th[k];
-                float gh = gsc * d1;
+                // with G1 = sum_a g1c_a hd_a + g2c_a hdd_a and G2 = sum_a g2c_a hd_a^2:
+                //   d loss / d w2_k = gsc t + s1 G1 + s2 G2        d loss / d h_k = w2 (gsc s1 + s2 G1 + s3 G2)
+                const float s1 = fmaf(-th[k], th[k], 1.f);
+                const float ws3 = -2.f * fmaf(ws1[k], s1, th[k] * ws2[k]);      // w2 s3
+                float G1 = 0.f, G2 = 0.f;
 #pragma unroll
                 for (int a = 0; a < DIM; ++a) {
-                    const float hd = acc[1 + a][t][k], hdd = acc[1 + DIM + a][t][k];
-                    gw2 += g1c[a] * d1 * hd + g2c[a] * (d2 * hd * hd + d1 * hdd);
-                    gh += g1c[a] * d2 * hd + g2c[a] * (d3 * hd * hd + d2 * hdd);
-                    acc[1 + a][t][k] = w2k[k] * (g1c[a] * d1 + g2c[a] * 2.f * d2 * hd);
-                    acc[1 + DIM + a][t][k] = w2k[k] * g2c[a] * d1;
+                    const float hd = h[1 + a][k];
+                    const float gh2 = g2c[a] * hd;
+                    G1 = fmaf(g1c[a], hd, fmaf(g2c[a], h[1 + DIM + a][k], G1));
+                    G2 = fmaf(gh2, hd, G2);
+                    h[1 + a][k] = fmaf(ws1[k], g1c[a], 2.f * ws2[k] * gh2);
+                    h[1 + DIM + a][k] = ws1[k] * g2c[a];
                 }
-                gh *= w2k[k];
-                acc[0][t][k] = gh;
+                const float gh = fmaf(ws3, G2, fmaf(ws2[k], G1, ws1[k] * gsc));
+                const float gw2 = fmaf(-2.f * th[k] * s1, G2, fmaf(s1, G1, gsc * th[k]));
+                h[0][k] = gh;
                 gb1acc[k] += gh;
                 gw2acc[k] += gw2;
             }
+            // the finished point enters the register tile at the top; after PPQ rounds point t sits in slot t
+#pragma unroll
+            for (int jt = 0; jt < J; ++jt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int s = 0; s + 1 < PPQ; ++s) acc[jt][s][k] = acc[jt][s + 1][k];
+                    acc[jt][PPQ - 1][k] = h[jt][k];
+                }
         }
 
-        // ---- C: scatter d loss / d H_jt into gVh: per corner  Wy u_x + Wx (+-beta)  (separable adjoint)
-        int l0x[PPQ], l0y[PPQ];                      // low corner of each point in cell 0 (window anchors)
-#pragma unroll
-        for (int t = 0; t < PPQ; ++t) { l0x[t] = 0; l0y[t] = 0; }
+        // ---- C: scatter d loss / d H_jt into gVh (separable adjoint: per corner  Wy u_x +- Wx beta), pre-reduced in
+        // registers over runs of consecutive points of this walker with identical corners
+#pragma unroll 1
         for (int n = 0; n < ncells; ++n) {
-            phase1(gcur, icur, n);
-            float* gcell = p.gVh + (long long)n * p.cell_stride + 4 * j;
-            float4* wn = win + (AGG ? n * 9 * L : 0);
-            int ox = 0, oy = 0, touched = 0;
-            if (AGG) { const int4 h = hdr[n]; ox = h.x; oy = h.y; touched = h.z; }
+            const float4* rec = recw + n * REC1;
+            float* gcell = p.gVh + (long long)n * p.T * K + 4 * j;
+            float cur[NCORN][4];
+            int cix[NCORN];
 #pragma unroll
             for (int t = 0; t < PPQ; ++t) {
                 const int ri = PPQ * q + t;
-                const float4 hd = rec[ri];
-                const int base = __float_as_int(hd.x);
-                const int mask = __float_as_int(hd.y);
-                const float4 ax = rec[1 * PTS + ri];
-                const float4 ay = rec[2 * PTS + ri];
+                int ix[NCORN];
+#pragma unroll
+                for (int hq = 0; hq < CQ; ++hq) {
+                    const float4 f = rec[hq * PTS + ri];
+                    ix[4 * hq] = __float_as_int(f.x); ix[4 * hq + 1] = __float_as_int(f.y);
+                    ix[4 * hq + 2] = __float_as_int(f.z); ix[4 * hq + 3] = __float_as_int(f.w);
+                }
+                const float4 ax = rec[CQ * PTS + ri];            // (w1, d, -e, w0)
+                const float4 ay = rec[(CQ + 1) * PTS + ri];
                 float cv[NCORN][4];
                 if (DIM == 2) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float alpha = acc[1][t][k] * ax.z - acc[3][t][k] * ax.w;
-                        const float beta = acc[2][t][k] * ay.z - acc[4][t][k] * ay.w;
-                        const float u0 = fmaf(acc[0][t][k], ax.x, -alpha);
-                        const float u1 = fmaf(acc[0][t][k], ax.y, alpha);
-                        const float bx0 = ax.x * beta, bx1 = ax.y * beta;
-                        cv[0][k] = fmaf(ay.x, u0, -bx0);
-                        cv[1][k] = fmaf(ay.x, u1, -bx1);
-                        cv[2][k] = fmaf(ay.y, u0, bx0);
-                        cv[3][k] = fmaf(ay.y, u1, bx1);
+                        const float alpha = fmaf(acc[3][t][k], ax.z, acc[1][t][k] * ax.y);
+                        const float beta = fmaf(acc[4][t][k], ay.z, acc[2][t][k] * ay.y);
+                        const float u0 = fmaf(acc[0][t][k], ax.w, -alpha);
+                        const float u1 = fmaf(acc[0][t][k], ax.x, alpha);
+                        const float bx0 = ax.w * beta, bx1 = ax.x * beta;
+                        cv[0][k] = fmaf(ay.w, u0, -bx0);
+                        cv[1][k] = fmaf(ay.w, u1, -bx1);
+                        cv[2][k] = fmaf(ay.x, u0, bx0);
+                        cv[3][k] = fmaf(ay.x, u1, bx1);
                     }
                 } else {
-                    const float4 az = rec[(DIM == 3 ? 3 : 2) * PTS + ri];
-                    const float p00 = ax.x * ay.x, p10 = ax.y * ay.x, p01 = ax.x * ay.y, p11 = ax.y * ay.y;
+                    const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTS + ri];
+                    const float p00 = ax.w * ay.w, p10 = ax.x * ay.w, p01 = ax.w * ay.x, p11 = ax.x * ay.x;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float alpha = acc[1][t][k] * ax.z - acc[1 + DIM][t][k] * ax.w;
-                        const float beta = acc[2][t][k] * ay.z - acc[(2 + DIM) % J][t][k] * ay.w;
-                        const float gamma = acc[DIM][t][k] * az.z - acc[2 * DIM][t][k] * az.w;
-                        const float u0 = fmaf(acc[0][t][k], ax.x, -alpha);
-                        const float u1 = fmaf(acc[0][t][k], ax.y, alpha);
-                        const float bx0 = ax.x * beta, bx1 = ax.y * beta;
-                        const float c00 = fmaf(ay.x, u0, -bx0), c10 = fmaf(ay.x, u1, -bx1);
-                        const float c01 = fmaf(ay.y, u0, bx0), c11 = fmaf(ay.y, u1, bx1);
-                        cv[0][k] = fmaf(az.x, c00, -p00 * gamma);
-                        cv[1][k] = fmaf(az.x, c10, -p10 * gamma);
-                        cv[2][k] = fmaf(az.x, c01, -p01 * gamma);
-                        cv[3][k] = fmaf(az.x, c11, -p11 * gamma);
-                        cv[4 % NCORN][k] = fmaf(az.y, c00, p00 * gamma);
-                        cv[5 % NCORN][k] = fmaf(az.y, c10, p10 * gamma);
-                        cv[6 % NCORN][k] = fmaf(az.y, c01, p01 * gamma);
-                        cv[7 % NCORN][k] = fmaf(az.y, c11, p11 * gamma);
+                        const float alpha = fmaf(acc[1 + DIM][t][k], ax.z, acc[1][t][k] * ax.y);
+                        const float beta = fmaf(acc[(2 + DIM) % J][t][k], ay.z, acc[2][t][k] * ay.y);
+                        const float gamma = fmaf(acc[2 * DIM][t][k], az.z, acc[DIM][t][k] * az.y);
+                        const float u0 = fmaf(acc[0][t][k], ax.w, -alpha);
+                        const float u1 = fmaf(acc[0][t][k], ax.x, alpha);
+                        const float bx0 = ax.w * beta, bx1 = ax.x * beta;
+                        const float c00 = fmaf(ay.w, u0, -bx0), c10 = fmaf(ay.w, u1, -bx1);
+                        const float c01 = fmaf(ay.x, u0, bx0), c11 = fmaf(ay.x, u1, bx1);
+                        cv[0][k] = fmaf(az.w, c00, -p00 * gamma);
+                        cv[1][k] = fmaf(az.w, c10, -p10 * gamma);
+                        cv[2][k] = fmaf(az.w, c01, -p01 * gamma);
+                        cv[3][k] = fmaf(az.w, c11, -p11 * gamma);
+                        cv[4 % NCORN][k] = fmaf(az.x, c00, p00 * gamma);
+                        cv[5 % NCORN][k] = fmaf(az.x, c10, p10 * gamma);
+                        cv[6 % NCORN][k] = fmaf(az.x, c01, p01 * gamma);
+                        cv[7 % NCORN][k] = fmaf(az.x, c11, p11 * gamma);
                     }
                 }
-                bool direct = true;
-                if (AGG) {
-                    const int lx = __float_as_int(hd.z), ly = __float_as_int(hd.w);
-                    if (n == 0) { l0x[t] = lx; l0y[t] = ly; }
-                    if (mask == FULL) {
-                        // cell n's low corner is that of cell 0 plus 0 or 1 per axis (the sub-texel multicell
-                        // offset), alternating from point to point inside one texel of cell 0: a window anchored
-                        // at cell 0's low corner covers both.  Re-anchor only when the point does not fit.
-                        int dx = lx - ox, dy = ly - oy;
-                        if ((unsigned)dx > 1u || (unsigned)dy > 1u) {
-                            if (touched) flush_window(wn, L, touched, ox, oy, gcell, K, p.size[0], p.size[1]);
-                            touched = 0;
-                            ox = l0x[t]; oy = l0y[t];
-                            dx = lx - ox; dy = ly - oy;
-                        }
-                        if ((unsigned)dx <= 1u && (unsigned)dy <= 1u) {
-                            const int s0 = dy * 3 + dx;
+                if (t > 0) {
+                    bool same = p.aggregate != 0;
 #pragma unroll
-                            for (int c = 0; c < NCORN; ++c) {
-                                float4* slot = wn + (s0 + (c & 1) + 3 * (c >> 1)) * L;
-                                float4 o = *slot;
-                                o.x += cv[c][0]; o.y += cv[c][1]; o.z += cv[c][2]; o.w += cv[c][3];
-                                *slot = o;
-                            }
-                            touched |= 0x1B << s0;
-                            direct = false;
-                        }
+                    for (int c = 0; c < NCORN; ++c) same = same && (ix[c] == cix[c]);
+                    if (same) {
+#pragma unroll
+                        for (int c = 0; c < NCORN; ++c)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) cv[c][k] += cur[c][k];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NCORN; ++c)
+                            red_add_v4(gcell + (long long)cix[c] * K, cur[c][0], cur[c][1], cur[c][2], cur[c][3]);
                     }
                 }
-                if (direct && mask) {
 #pragma unroll
-                    for (int c = 0; c < NCORN; ++c)
-                        if ((mask >> c) & 1)
-                            red_add_v4(gcell + (long long)(base + coff[c]) * K, cv[c][0], cv[c][1], cv[c][2], cv[c][3]);
+                for (int c = 0; c < NCORN; ++c) {
+                    cix[c] = ix[c];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cur[c][k] = cv[c][k];
                 }
             }
-            if (AGG) {
-                __syncwarp();
-                if (j == 0) hdr[n] = make_int4(ox, oy, touched, 0);
+#pragma unroll
+            for (int c = 0; c < NCORN; ++c)
+                red_add_v4(gcell + (long long)cix[c] * K, cur[c][0], cur[c][1], cur[c][2], cur[c][3]);
+        }
+
+        if (have_next) {
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+                icur[u] = inext[u];
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) gcur[u][a] = gnext[u][a];
             }
         }
-
-        if (!have_next) break;
-#pragma unroll
-        for (int u = 0; u < PPL; ++u) {
-            icur[u] = inext[u];
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) gcur[u][a] = gnext[u][a];
-        }
-    }
-
-    if (AGG) {
-        __syncwarp();
-        for (int n = 0; n < ncells; ++n) {
-            const int4 h = hdr[n];
-            if (h.z) flush_window(win + n * 9 * L, L, h.z, h.x, h.y, p.gVh + (long long)n * p.cell_stride + 4 * j, K,
-                                  p.size[0], p.size[1]);
-        }
-    }
     }
 
     // ---- head-parameter gradients and loss: walkers of a warp (shuffles) -> warps (shared memory) -> one
@@ -711,9 +728,9 @@ cs_pde_fused_kernel(const FusedParams p) {
         gb2acc += __shfl_xor_sync(0xffffffffu, gb2acc, o);
         lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
     }
-    __syncthreads();                                 // every warp is done with its records / windows
+    __syncthreads();                                 // every warp is done with its records
     float* red = reinterpret_cast<float*>(smem4);    // [wpb][2K + 2]
-    const int RW = 2 * K + 2;
+    constexpr int RW = 2 * K + 2;
     if (q == 0) {
         float* rw = red + warp * RW;
 #pragma unroll
@@ -732,26 +749,21 @@ cs_pde_fused_kernel(const FusedParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------------
-inline int fused_win_stride(int N, int L) {
-    int s = N * 9 * L;
-    s += (4 - (s % 8) + 8) % 8;          // walker stride = 4 mod 8 float4: neighbouring walkers use opposite bank halves
-    return s;
-}
-
-template <int DIM, int LSHIFT, bool AGG>
+template <int DIM, int LSHIFT>
 cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
-    constexpr int L = 1 << LSHIFT;
     constexpr int NW = 32 >> LSHIFT;
+    constexpr int K = 4 << LSHIFT;
     constexpr int PPQ = (DIM == 2) ? 4 : 2;
     constexpr int PTS = PPQ * NW;
-    constexpr int REC1 = (1 + DIM) * PTS;
-    auto kern = cs_pde_fused_kernel<DIM, LSHIFT, AGG>;
-    const int threads = AGG ? FUSED_THREADS_AGG : FUSED_THREADS;
-    const int wpb = threads / 32;
-    p.win_stride = AGG ? fused_win_stride(p.N, L) : 0;
-    const size_t per_warp = (size_t)(REC1 + (AGG ? NW * p.win_stride + NW * p.N : 0)) * sizeof(float4);
+    constexpr int REC1 = ((1 << DIM) / 4 + DIM) * PTS;
+    auto kern = cs_pde_fused_kernel<DIM, LSHIFT>;
+    if (p.N > FUSED_MAX_CELLS) return cudaErrorInvalidConfiguration;
+    const size_t per_warp = (size_t)p.N * REC1 * sizeof(float4);
+    int wpb = FUSED_THREADS / 32;
+    while (wpb > 1 && wpb * per_warp > 72 * 1024) wpb >>= 1;      // three blocks per SM where the records allow
+    const int threads = wpb * 32;
     size_t smem = wpb * per_warp;
-    const size_t red_bytes = (size_t)wpb * (2 * p.K + 2) * sizeof(float);
+    const size_t red_bytes = (size_t)wpb * (2 * K + 2) * sizeof(float);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     int dev = 0;
@@ -765,26 +777,12 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    long long blocks = (long long)sms * occ;
     p.num_ptiles = (p.P + PTS - 1) / PTS;
-    if (AGG) {
-        // every walker owns pts_per_walker contiguous points; short inputs use fewer blocks so that a walker
-        // still sees a few texels' worth of points
-        long long walkers = blocks * wpb * NW;
-        long long R = (p.P + walkers - 1) / walkers;
-        const long long minR = 8 * PPQ;
-        if (R < minR) {
-            R = minR;
-            walkers = (p.P + R - 1) / R;
-            blocks = (walkers + wpb * NW - 1) / (wpb * NW);
-        }
-        R = (R + PPQ - 1) / PPQ * PPQ;
-        p.pts_per_walker = R;
-    } else {
-        const long long need = (p.num_ptiles + wpb - 1) / wpb;
-        if (blocks > need) blocks = need;
-    }
+    long long blocks = (long long)sms * occ;
+    const long long need = (p.num_ptiles + wpb - 1) / wpb;
+    if (blocks > need) blocks = need;
     if (blocks < 1) return cudaSuccess;
+    p.tiles_per_warp = (p.num_ptiles + blocks * wpb - 1) / (blocks * wpb);
     kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -11,10 +11,5 @@
 #define CS_FN CS_CAT(launch_fused_d, CS_DIM, _l, CS_LSHIFT)
 
 namespace cs {
-cudaError_t CS_FN(bool aggregate, FusedParams& p, cudaStream_t s) {
-#if CS_DIM == 2
-    if (aggregate) return launch_fused_one<2, CS_LSHIFT, true>(p, s);
-#endif
-    return launch_fused_one<CS_DIM, CS_LSHIFT, false>(p, s);
-}
+cudaError_t CS_FN(FusedParams& p, cudaStream_t s) { return launch_fused_one<CS_DIM, CS_LSHIFT>(p, s); }
 }  // namespace cs

@@ -73,7 +73,7 @@ class PointShardedStep:
                 # the one-pass step scatters into the W1-mixed cells: K hidden units per texel
                 from .fused import head_params, small_buffer_size
                 K = head_params(head, cells.shape[1])[0].shape[0]
-                self.reducer = PeerReducer(cells, small_buffer_size(cells.shape[1], K), group, channels=K)
+                self.reducer = PeerReducer(cells, small_buffer_size(cells.shape[1], K), group, channels=K, tail=K)
             elif self.mode == "jets":
                 from .jet import head_buffer_size
                 self.reducer = PeerReducer(cells, head_buffer_size(cells.shape[1]), group)

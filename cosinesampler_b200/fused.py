@@ -114,13 +114,14 @@ def bin_points(cells, coords, offset=None, align_corners=True, multicell=True, w
 
 
 def head_premix(cells, W1):
-    """Vh [N, T, K] = W1 applied to cells [N, C, *S] texel by texel (cs_head_premix)."""
+    """Vh [N*T + 1, K]: W1 applied to cells [N, C, *S] texel by texel, plus one zero texel that
+    out-of-bounds corners read (cs_head_premix).  `Vh[:N*T].view(N, T, K)` is the mixed stack."""
     ops._check(cells, "input")
     ops._check(W1, "W1")
     N, C = cells.shape[:2]
     K = W1.shape[0]
     T = cells[0, 0].numel() if N and C else 0
-    Vh = torch.empty((N, T, K), dtype=cells.dtype, device=cells.device)
+    Vh = torch.empty((N * T + 1, K), dtype=cells.dtype, device=cells.device)
     with ops._on_device(cells.device), ops._timed("PREMIX", 4 * N * T * (C + K), cells.device):
         rc = _lib.load().cs_head_premix(N, C, T, K, cells.data_ptr(), W1.data_ptr(), Vh.data_ptr(),
                                         ops._cur_stream(cells.device))
@@ -150,8 +151,9 @@ def fused_bytes(dim, N, K, P, T):
 
 
 class OnePassPdeStep:
-    """See the module docstring.  aggregate: 'auto' (shared-memory aggregation windows when the kernel has
-    them for this shape), 'off' (one red per corner), 'force'.  bin: sort every chunk by texel first."""
+    """See the module docstring.  aggregate: 'auto' / 'on' (runs of consecutive points with identical corners
+    leave as one red per corner) or 'off' (one red per corner and point).  bin: sort every chunk by texel
+    (and sub-texel quadrant) first."""
 
     def __init__(self, cells, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
                  align_corners=True, kernel="cosine", multicell=True, bin=True, aggregate="auto"):
@@ -169,7 +171,7 @@ class OnePassPdeStep:
         self.params = head_params(head, cells.shape[1])
         self.K = self.params[0].shape[0]
         self.bin = bool(bin)
-        self.aggregate = {"off": 0, "auto": 1, "force": 2}[aggregate]
+        self.aggregate = {"off": 0, "auto": 1, "on": 1}[aggregate]
         self.res = residual_coefficients(residual, self.dim, k2)
         self._live = False
 
@@ -188,7 +190,8 @@ class OnePassPdeStep:
                 self.acc = reducer.accumulator()
                 self.buf = reducer.small_buffer()
             else:
-                self.acc = torch.zeros((N, self.T, self.K), dtype=torch.float32, device=self.cells.device)
+                # one extra texel absorbs the contributions of out-of-bounds corners
+                self.acc = torch.zeros((N * self.T + 1, self.K), dtype=torch.float32, device=self.cells.device)
                 self.buf = torch.zeros(small_buffer_size(C, self.K), dtype=torch.float32, device=self.cells.device)
         self.scale = None if scale is None else float(scale)
         self._live = True

@@ -25,11 +25,15 @@ profiler = None
 
 
 class _timed:
-    """Brackets one stage call with CUDA events when a profiler is installed."""
-    __slots__ = ("label", "nbytes", "device", "start")
+    """Brackets one stage call with CUDA events when a profiler is installed.
+    nbytes: algorithmic bytes (every boundary tensor once, an expanded gOut counted
+    as the N-fold tensor the reference materialises); moved: the bytes the launch really has to move (an
+    expanded stream once), reported beside it."""
+    __slots__ = ("label", "nbytes", "device", "start", "moved")
 
-    def __init__(self, label, nbytes, device):
+    def __init__(self, label, nbytes, device, moved=None):
         self.label, self.nbytes, self.device, self.start = label, nbytes, device, None
+        self.moved = nbytes if moved is None else moved
 
     def __enter__(self):
         if profiler is not None:
@@ -41,15 +45,21 @@ class _timed:
         if self.start is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record(torch.cuda.current_stream(self.device))
-            profiler.record(self.label, self.nbytes, self.start, end)
+            try:
+                profiler.record(self.label, self.nbytes, self.start, end, self.moved)
+            except TypeError:                      # a profiler with the 4-argument signature
+                profiler.record(self.label, self.nbytes, self.start, end)
 
 
-def algorithmic_bytes(dim, N, C, P, T, streams, per_point, fields):
+def algorithmic_bytes(dim, N, C, P, T, streams, per_point, fields, expanded_streams=0):
     """Algorithmic bytes of one stage call: every tensor crossing the
     operator boundary counted once.  streams = number of [N,C,P] tensors read or written,
     per_point = number of [N,P,dim] tensors (coordinates included), fields = number of
-    grid-shaped [N,C,T] tensors read or produced."""
-    return 4 * (N * P * (C * streams + dim * per_point) + fields * N * C * T)
+    grid-shaped [N,C,T] tensors read or produced.  expanded_streams of the `streams` are stride-0
+    over the cells (PIXEL's `val.sum(0)` gradient): they are counted once instead of N times, which
+    gives the bytes a launch really moves."""
+    full = streams - expanded_streams
+    return 4 * (P * (C * (N * full + expanded_streams) + N * dim * per_point) + fields * N * C * T)
 
 
 def set_index_mode(mode):
@@ -207,7 +217,7 @@ def to_channel_last(field):
     N, C = field.shape[:2]
     T = field[0, 0].numel() if N > 0 and C > 0 else 0
     cl = torch.empty((N, T, C), dtype=field.dtype, device=field.device)
-    with _on_device(field.device):
+    with _on_device(field.device), _timed("AUX[to_channel_last]", 8 * N * T * C, field.device):
         rc = _lib.load().cs_to_channel_last(field.data_ptr(), cl.data_ptr(), N, C, T,
                                             _cur_stream(field.device))
     _lib.check(rc, "cs_to_channel_last")
@@ -221,7 +231,7 @@ def from_channel_last(cl, shape, out=None, accumulate=False):
     if out is None:
         out = torch.empty(shape, dtype=cl.dtype, device=cl.device)
         accumulate = False
-    with _on_device(cl.device):
+    with _on_device(cl.device), _timed("AUX[from_channel_last]", 8 * N * T * C, cl.device):
         rc = _lib.load().cs_from_channel_last(cl.data_ptr(), out.data_ptr(), N, C, T,
                                               1 if accumulate else 0, _cur_stream(cl.device))
     _lib.check(rc, "cs_from_channel_last")
@@ -262,10 +272,11 @@ def _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multice
 
 def _new_accumulator(input, layout):
     N, C = input.shape[:2]
-    if layout == _lib.LAYOUT_CHANNEL_LAST:
-        T = input[0, 0].numel() if N > 0 and C > 0 else 0
-        return torch.zeros((N, T, C), dtype=input.dtype, device=input.device)
-    return torch.zeros_like(input, memory_format=torch.contiguous_format)
+    with _timed("AUX[zero accumulator]", 4 * input.numel(), input.device):
+        if layout == _lib.LAYOUT_CHANNEL_LAST:
+            T = input[0, 0].numel() if N > 0 and C > 0 else 0
+            return torch.zeros((N, T, C), dtype=input.dtype, device=input.device)
+        return torch.zeros_like(input, memory_format=torch.contiguous_format)
 
 
 def _finish_accumulator(acc, input, layout):
@@ -312,9 +323,11 @@ def backward(gOut, input, grid, offset, padding_mode, align_corners, input_requi
     gGrid = torch.empty(tuple(grid.shape), dtype=input.dtype, device=input.device) if want_grid else None
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
     label = "B%dd[%s%s]" % (dim, "I" if acc is not None else "", "G" if want_grid else "")
-    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, streams=1, per_point=1 + (1 if want_grid else 0),
-                               fields=(1 if want_grid else 0) + (1 if acc is not None else 0))
-    with _on_device(input.device), _timed(label, nbytes, input.device):
+    bkw = dict(streams=1, per_point=1 + (1 if want_grid else 0),
+               fields=(1 if want_grid else 0) + (1 if acc is not None else 0))
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, **bkw)
+    moved = algorithmic_bytes(dim, N, C, P, D * H * W, expanded_streams=1 if gs.stride_n == 0 and N > 1 else 0, **bkw)
+    with _on_device(input.device), _timed(label, nbytes, input.device, moved):
         rc = _lib.load().cs_backward(pb, gs, field.data_ptr() if field is not None else None,
                                      grid.data_ptr(), offset.data_ptr(),
                                      acc.data_ptr() if acc is not None else None,
@@ -355,11 +368,11 @@ def backward_backward(gOutInput, gOutGrid, input, grid, gOut, offset, padding_mo
     pb = _problem(dim, N, C, D, H, W, P, padding_mode, align_corners, kernel, multicell, layout, grid_sn)
     label = "BB%dd[%s%s%s%s]" % (dim, "I" if want_input else "", "G" if want_grid else "",
                                  "O" if want_ggout else "", "+U" if goi is not None else "")
-    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, streams=1 + (1 if want_ggout else 0),
-                               per_point=2 + (1 if want_grid else 0),
-                               fields=(1 if need_field else 0) + (1 if want_input else 0)
-                               + (1 if goi is not None else 0))
-    with _on_device(input.device), _timed(label, nbytes, input.device):
+    bkw = dict(streams=1 + (1 if want_ggout else 0), per_point=2 + (1 if want_grid else 0),
+               fields=(1 if need_field else 0) + (1 if want_input else 0) + (1 if goi is not None else 0))
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, **bkw)
+    moved = algorithmic_bytes(dim, N, C, P, D * H * W, expanded_streams=1 if gs.stride_n == 0 and N > 1 else 0, **bkw)
+    with _on_device(input.device), _timed(label, nbytes, input.device, moved):
         rc = _lib.load().cs_backward_backward(
             pb, goi.data_ptr() if goi is not None else None, gOutGrid.data_ptr(),
             field.data_ptr() if field is not None else None, grid.data_ptr(), gs, offset.data_ptr(),
@@ -401,10 +414,12 @@ def backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, p
     fused = gs2.ptr is not None
     label = "BBB%dd[%s%s%s]" % (dim, "I" if want_input else "", "O" if want_ggout else "",
                                 "+X2" if fused else "")
-    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W,
-                               streams=1 + (1 if want_ggout else 0) + (1 if fused else 0), per_point=3,
-                               fields=(1 if want_ggout else 0) + (1 if want_input else 0))
-    with _on_device(input.device), _timed(label, nbytes, input.device):
+    bkw = dict(streams=1 + (1 if want_ggout else 0) + (1 if fused else 0), per_point=3,
+               fields=(1 if want_ggout else 0) + (1 if want_input else 0))
+    nbytes = algorithmic_bytes(dim, N, C, P, D * H * W, **bkw)
+    nexp = (1 if gs.stride_n == 0 and N > 1 else 0) + (1 if fused and gs2.stride_n == 0 and N > 1 else 0)
+    moved = algorithmic_bytes(dim, N, C, P, D * H * W, expanded_streams=nexp, **bkw)
+    with _on_device(input.device), _timed(label, nbytes, input.device, moved):
         rc = _lib.load().cs_backward_backward_backward(
             pb, field.data_ptr() if field is not None else None, grid.data_ptr(), gs,
             gOutGrid.data_ptr(), gOutgGrid.data_ptr(), gs2, offset.data_ptr(),

@@ -23,9 +23,11 @@ MAX_PEERS = 8
 class PeerReducer:
     """Symmetric buffers + the fused reduce for one `cells` shape and one process group."""
 
-    def __init__(self, cells, n_small, group=None, channels=None):
+    def __init__(self, cells, n_small, group=None, channels=None, tail=0):
         """channels: channel count of the accumulator when it differs from the cells' (the one-pass step
-        scatters into the W1-mixed cells: K hidden units per texel instead of C channels)."""
+        scatters into the W1-mixed cells: K hidden units per texel instead of C channels).
+        tail: extra floats allocated behind the accumulator (the one-pass step's dump texel); they are zeroed
+        with it and never reduced."""
         import torch.distributed._symmetric_memory as symm_mem
         if not dist.is_initialized():
             raise RuntimeError("PeerReducer needs an initialised process group")
@@ -41,7 +43,8 @@ class PeerReducer:
         self.n_small = int(n_small)
         dev = cells.device
         n = self.N * self.T * self.C
-        self.acc = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.acc = symm_mem.empty(n + int(tail), dtype=torch.float32, device=dev)
+        self._n = n
         self.out = symm_mem.empty(n, dtype=torch.float32, device=dev)
         self.small = symm_mem.empty(max(self.n_small, 4), dtype=torch.float32, device=dev)
         self.h_acc = symm_mem.rendezvous(self.acc, group)
@@ -60,7 +63,7 @@ class PeerReducer:
 
     def accumulator(self):
         """The zeroed channel-last accumulator [N, T, C] of this step (zeroed after the previous reduce)."""
-        return self.acc.view(self.N, self.T, self.C)
+        return self.acc[:self._n].view(self.N, self.T, self.C)
 
     def small_buffer(self):
         """The zeroed small vector (head gradients | loss) of this step."""

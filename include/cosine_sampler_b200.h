@@ -168,9 +168,10 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float *jets, const
  * linear, so they commute: the cells are mixed with W1 once per step (cs_head_premix), the gather then
  * delivers the hidden pre-activations, the adjoint scatters d loss / d hidden into gVh, and cs_head_postmix
  * returns gInput = W1^T gVh and gW1 = sum_texels gVh (x) input.  Points may be given in any order; binned
- * by texel (cs_bin_points) the kernel gathers from cache and pre-reduces its scatter in shared memory. */
+ * by texel (cs_bin_points) the kernel gathers from cache and pre-reduces its scatter in registers. */
 
-/* Counting sort of coords [P, dim] on a tile-major texel key (8x8 texels in 2D, 4x4x4 in 3D) of cell 0.
+/* Counting sort of coords [P, dim] on a tile-major texel key (8x8 texels in 2D, 4x4x4 in 3D) of cell 0,
+ * refined by the sub-texel quadrant when the point density allows (>= 4 points per sub-bin).
  * sorted [P, dim]; perm [P] (nullable): perm[i] = index in coords of sorted point i.  offset [N] device
  * (nullable).  workspace: cs_bin_workspace_bytes() bytes of device scratch.  Order inside a bin is not
  * deterministic.  Uses pb->dim, D/H/W, P, align_corners, multicell, index_mode. */
@@ -178,8 +179,9 @@ int cs_bin_workspace_bytes(const cs_problem *pb, int64_t *bytes);
 int cs_bin_points(const cs_problem *pb, const float *coords, const float *offset, float *sorted,
                   int32_t *perm, void *workspace, int64_t workspace_bytes, void *stream);
 
-/* Vh [N, T, K] = W1 [K, C] applied to input [N, C, T] texel by texel (channel-first in, channel-last out:
- * the staging transpose and the first Linear layer, test_2d.py:44, in one pass).  K in {4, 8, 16, 32}, C <= 64. */
+/* Vh [N*T + 1, K]: Vh[n*T + t, :] = W1 [K, C] applied to input [n, :, t] (channel-first in, channel-last out:
+ * the staging transpose and the first Linear layer, test_2d.py:44, in one pass); the extra texel Vh[N*T, :] is
+ * set to zero -- out-of-bounds corners of cs_pde_fused_step read it.  K in {4, 8, 16, 32}, C <= 64. */
 int cs_head_premix(int32_t N, int32_t C, int64_t T, int32_t K, const float *input, const float *W1,
                    float *Vh, void *stream);
 /* gInput [N, C, T] (= or +=, nullable) = W1^T gVh;  gW1 [K, C] (+=, nullable) = sum_{n,t} gVh[n,t,:] (x) input[n,:,t].
@@ -193,12 +195,13 @@ int cs_head_postmix(int32_t N, int32_t C, int64_t T, int32_t K, const float *gVh
  * pb->field_layout = CS_LAYOUT_CHANNEL_LAST, P = number of points; coords [P, dim] shared by all cells.
  * Residual f = c_u u + c_u3 u^3 + sum_a (c1[a] u_a + c2[a] u_aa) with u = w2 . tanh(H + b1) + b2 and H the
  * sampled mixed cells summed over the N cells; loss_sum [1] += sum_p f^2 (unscaled); gradients of
- * scale * sum_p f^2: gVh [N, T, K] += (zero-initialised by the caller), gb1 [K] +=, gw2 [K] +=, gb2 [1] +=.
- * aggregate: 0 = one red.global.add.v4.f32 per (cell, point, corner); 1 = auto: walker-private 3x3-texel
- * windows in shared memory when dim == 2 and they fit (meant for binned points); 2 = require them. */
-struct cs_pde_residual;
+ * scale * sum_p f^2: gVh [N*T + 1, K] += (zero-initialised by the caller; like Vh it carries one extra texel,
+ * which absorbs the contributions of out-of-bounds corners and is to be ignored), gb1 [K] +=, gw2 [K] +=,
+ * gb2 [1] +=.  Vh is the [N*T + 1, K] output of cs_head_premix.
+ * aggregate: 0 = one red.global.add.v4.f32 per (cell, point, corner); 1 = contributions of consecutive
+ * points with identical corners are summed in registers first (pays with binned points). */
 int cs_pde_fused_step(const cs_problem *pb, const float *Vh, const float *coords, const float *offset,
-                      const float *b1, const float *w2, const float *b2, const struct cs_pde_residual *res,
+                      const float *b1, const float *w2, const float *b2, const cs_pde_residual *res,
                       float scale, float *gVh, float *gb1, float *gw2, float *gb2, float *loss_sum,
                       int32_t aggregate, void *stream);
 

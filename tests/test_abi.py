@@ -117,3 +117,38 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
                                 None, None, None, None, None, None, None, None) == -1
     assert lib.cs_peer_allreduce_from_channel_last(9, 0, None, None, 1, 8, 64, None, None, 0, None) == -2
     assert lib.cs_peer_allreduce_from_channel_last(2, 0, None, None, 1, 8, 64, None, None, 0, None) == -1
+
+
+def test_one_pass_entry_points_validate_arguments_without_a_gpu():
+    """cs_bin_* / cs_head_*mix / cs_pde_fused_step reject bad problems before any CUDA call, and the binning
+    workspace size is a pure host computation."""
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    pb = _lib.Problem()
+    pb.dim, pb.N, pb.C, pb.D, pb.H, pb.W, pb.P = 2, 4, 16, 1, 256, 256, 2 ** 22
+    pb.align_corners, pb.multicell = 1, 1
+    n = ctypes.c_int64(0)
+    assert lib.cs_bin_workspace_bytes(ctypes.byref(pb), ctypes.byref(n)) == 0
+    # 65 points per texel: 16 sub-bins per texel -> 2^20 bins, one rank word per point
+    assert n.value >= 4 * (2 ** 20 + 2 ** 22)
+    pb.P = 2 ** 31
+    assert lib.cs_bin_workspace_bytes(ctypes.byref(pb), ctypes.byref(n)) == -2
+    pb.P = 64
+    assert lib.cs_bin_points(ctypes.byref(pb), None, None, None, None, None, 0, None) == -1
+    assert b"NULL" in lib.cs_last_error()
+    assert lib.cs_head_premix(4, 16, 64, 12, None, None, None, None) == -2
+    assert b"hidden width" in lib.cs_last_error()
+    assert lib.cs_head_premix(4, 65, 64, 16, None, None, None, None) == -2
+    assert lib.cs_head_premix(4, 16, 64, 16, None, None, None, None) == -1
+    assert lib.cs_head_postmix(4, 16, 64, 16, None, 0, None, None, None, 0, None, None) == -1
+    res = _lib.PdeResidual()
+    pb.field_layout = _lib.LAYOUT_CHANNEL_FIRST
+    args = (None, None, None, None, None, None, ctypes.byref(res), 1.0, None, None, None, None, None, 1, None)
+    assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == -2            # needs the mixed, channel-last cells
+    pb.field_layout = _lib.LAYOUT_CHANNEL_LAST
+    pb.C = 12
+    assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == -2 and b"hidden width" in lib.cs_last_error()
+    pb.C = 16
+    assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == -1 and b"NULL" in lib.cs_last_error()
+    pb.P = 0
+    assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == 0             # empty problem: nothing to launch
