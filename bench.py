@@ -206,7 +206,7 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
     # a chunk holds, the more of them share a texel and the fewer reds leave the SMs); the end-to-end arm cuts
     # the shard into pieces so that the host->device copy of one piece overlaps the pass over the previous one
     fchunk = max(1, nloc)
-    fchunk_e2e = max(2 ** 20, (nloc + 3) // 4)
+    fchunk_e2e = max(2 ** 20, (nloc + 7) // 8)
     reduce_kind = "none (single GPU)"
     fstepper = None
     want_peer = world > 1 and not args.nccl_reduce
@@ -223,7 +223,7 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
         if float(vote.item()) > 0.5:
             fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw,
                                            peer_reduce=True)
-            reduce_kind = "peer-memory kernel cs_peer_allreduce_from_channel_last (symmetric memory over NVLink)"
+            reduce_kind = "peer-memory kernel: " + fstepper.reducer.kind
     if fstepper is None:
         fstepper = dp.PointShardedStep(None, cells, head, residual=residual, chunk=fchunk, fused=fused_kw)
         if world > 1:

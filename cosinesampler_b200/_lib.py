@@ -15,6 +15,7 @@ EXPORTS = (
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
     "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step", "cs_peer_allreduce_from_channel_last",
+    "cs_peer_allreduce",
     "cs_bin_workspace_bytes", "cs_bin_points", "cs_head_premix", "cs_head_postmix", "cs_pde_fused_step",
 )
 
@@ -89,6 +90,8 @@ def load():
                                      ctypes.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cs_peer_allreduce_from_channel_last.restype = ctypes.c_int
     lib.cs_peer_allreduce_from_channel_last.argtypes = [i32, i32, vp, vp, i32, i32, i64, vp, vp, i32, vp]
+    lib.cs_peer_allreduce.restype = ctypes.c_int
+    lib.cs_peer_allreduce.argtypes = [i32, i32, vp, vp, i64, vp, vp, vp, vp, i32, vp]
     lib.cs_bin_workspace_bytes.restype = ctypes.c_int
     lib.cs_bin_workspace_bytes.argtypes = [pp, ctypes.POINTER(ctypes.c_int64)]
     lib.cs_bin_points.restype = ctypes.c_int

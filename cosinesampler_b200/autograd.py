@@ -112,21 +112,49 @@ def _pop_want(default):
     return default if w is None else w
 
 
+# Dead-output elision rests on a private torch API.  It is probed once at import: when it is missing every
+# backward computes every output again (correct, but the u_x / u_xx evaluations pay their dead gInput scatters:
+# a large slowdown), and that is said once instead of silently.  tests/test_gpu_chain.py pins the launch counts.
+_HAVE_EXEC_INFO = hasattr(torch._C, "_will_engine_execute_node")
+_warned_exec_info = False
+
+
+def _warn_no_exec_info(why):
+    global _warned_exec_info
+    if not _warned_exec_info:
+        _warned_exec_info = True
+        import warnings
+        warnings.warn("cosinesampler_b200: cannot ask the autograd engine which outputs it needs (%s); "
+                      "every backward stage computes all its outputs (slower, same results)" % why)
+
+
+if not _HAVE_EXEC_INFO:
+    _warn_no_exec_info("torch._C._will_engine_execute_node is missing in torch %s" % torch.__version__)
+
+
 def _engine_wants(ctx, idx):
-    """Will the engine consume the gradient we return for input `idx` in this pass?"""
+    """Will the engine consume the gradient we return for input `idx` in this pass?
+    `idx` indexes the forward's inputs: the tensor arguments come FIRST in every forward signature of this
+    module (input, grid, gOut, ...), so `ctx.next_functions[idx]` is the edge of that tensor."""
     if not ctx.needs_input_grad[idx]:
         return False
+    if not _HAVE_EXEC_INFO:
+        return True
     try:
         fn = ctx.next_functions[idx][0]
-    except Exception:
+    except Exception as exc:
+        _warn_no_exec_info("ctx.next_functions: %s" % exc)
         return True
     if fn is None:
         return False
     try:
         return bool(torch._C._will_engine_execute_node(fn))
-    except Exception:
-        # leaf captured by autograd.grad (the call raises for it) or an engine
-        # without exec info: assume needed
+    except RuntimeError:
+        # the documented case: a leaf captured by autograd.grad, or a pass without exec info
+        # (plain .backward()): the call raises and the gradient is needed
+        return True
+    except Exception as exc:
+        _warn_no_exec_info("%s: %s" % (type(exc).__name__, exc))
         return True
 
 

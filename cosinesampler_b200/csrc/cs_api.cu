@@ -265,12 +265,19 @@ struct PeerParams {
     const float* small_in[CS_MAX_PEERS];
     float* small_out;
     int world, rank, N, C, small_n, tiles_y;
+    int vec4;                   // every accumulator is 16-byte aligned
     long long T, tiles_x, total_tiles, my_tiles;
 };
 
 __device__ __forceinline__ float ld_peer(const float* p) {
     float v;
     asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 
@@ -286,13 +293,30 @@ __global__ void __launch_bounds__(256) cs_peer_reduce_kernel(const PeerParams p)
         const long long t0 = bx * 32;
         const int c0 = by * 32;
         const int ct = min(32, p.C - c0);
-        for (int idx = threadIdx.x; idx < 32 * ct; idx += 256) {
-            const int t = idx / ct, c = idx - t * ct;
-            if (t0 + t < p.T) {
-                const long long off = ((long long)n * p.T + t0 + t) * p.C + c0 + c;
-                float s = 0.f;
-                for (int r = 0; r < p.world; ++r) s += ld_peer(p.acc[r] + off);
-                tile[c][t] = s;
+        if ((ct & 3) == 0 && (p.C & 3) == 0 && p.vec4) {
+            // 16-byte peer loads: a texel's channels are contiguous
+            const int cq = ct >> 2;
+            for (int idx = threadIdx.x; idx < 32 * cq; idx += 256) {
+                const int t = idx / cq, c = 4 * (idx - t * cq);
+                if (t0 + t < p.T) {
+                    const long long off = ((long long)n * p.T + t0 + t) * p.C + c0 + c;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < p.world; ++r) {
+                        const float4 v = ld_peer_v4(p.acc[r] + off);
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
+                    tile[c][t] = s.x; tile[c + 1][t] = s.y; tile[c + 2][t] = s.z; tile[c + 3][t] = s.w;
+                }
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < 32 * ct; idx += 256) {
+                const int t = idx / ct, c = idx - t * ct;
+                if (t0 + t < p.T) {
+                    const long long off = ((long long)n * p.T + t0 + t) * p.C + c0 + c;
+                    float s = 0.f;
+                    for (int r = 0; r < p.world; ++r) s += ld_peer(p.acc[r] + off);
+                    tile[c][t] = s;
+                }
             }
         }
         __syncthreads();
@@ -309,6 +333,67 @@ __global__ void __launch_bounds__(256) cs_peer_reduce_kernel(const PeerParams p)
             float s = 0.f;
             for (int r = 0; r < p.world; ++r) s += ld_peer(p.small_in[r] + i);
             p.small_out[i] = s;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// Layout-preserving all-reduce over peer memory (the one-pass step: its accumulator is consumed channel-last by
+// cs_head_postmix, so nothing has to be transposed).  The buffer is cut into 16-byte words dealt to the ranks
+// in contiguous slices; the owner of a slice sums it over all ranks and stores the sum into every rank's
+// output.  Two data paths:
+//   * multimem (NVSwitch multicast objects, sm_90+): ONE multimem.ld_reduce.add.v4.f32 returns the sum of all
+//     ranks' copies, reduced inside the switch, and ONE multimem.st.v4.f32 broadcasts it: every byte crosses
+//     this GPU's links once in each direction whatever the world size;
+//   * peer pointers: world 16-byte ld.volatile loads in rank order and world 16-byte stores.
+// ---------------------------------------------------------------------------
+struct PeerFlatParams {
+    const float* acc[CS_MAX_PEERS];
+    float* out[CS_MAX_PEERS];
+    const float* small_in[CS_MAX_PEERS];
+    const float* acc_mc;        // multicast address of the accumulators (nullptr: peer-pointer path)
+    float* out_mc;              // multicast address of the outputs
+    float* small_out;
+    int world, rank, small_n;
+    long long n4;               // 16-byte words in the buffer
+    long long begin4, end4;     // this rank's slice
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_v4(float* p, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool MULTIMEM>
+__global__ void __launch_bounds__(256) cs_peer_flat_reduce_kernel(const PeerFlatParams p) {
+    if (blockIdx.x + 1 == gridDim.x && p.small_n > 0) {
+        // the last block sums the small vector (head gradients, loss) of all ranks for this rank
+        for (int i = threadIdx.x; i < p.small_n; i += 256) {
+            float s = 0.f;
+            for (int r = 0; r < p.world; ++r) s += ld_peer(p.small_in[r] + i);
+            p.small_out[i] = s;
+        }
+        return;
+    }
+    const long long stride = (long long)(gridDim.x - (p.small_n > 0 ? 1 : 0)) * 256;
+    for (long long w = p.begin4 + (long long)blockIdx.x * 256 + threadIdx.x; w < p.end4; w += stride) {
+        if (MULTIMEM) {
+            const float4 v = multimem_ld_reduce_v4(p.acc_mc + 4 * w);
+            multimem_st_v4(p.out_mc + 4 * w, v);
+        } else {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.world; ++r) {
+                const float4 v = ld_peer_v4(p.acc[r] + 4 * w);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            for (int r = 0; r < p.world; ++r) *reinterpret_cast<float4*>(p.out[r] + 4 * w) = s;
         }
     }
 }
@@ -558,7 +643,7 @@ int cs_bin_workspace_bytes(const cs_problem* pb, int64_t* bytes) {
     if (int rc = bin_setup(pb, b)) return rc;
     if (!bytes) return fail(CS_EINVAL, "cs_bin_workspace_bytes: bytes is NULL");
     *bytes = round256((long long)b.nbins * 4) + round256(((long long)b.nbins / cs::BIN_SCAN_CHUNK + 1) * 4) +
-             round256((long long)pb->P * 4);
+             2 * round256((long long)pb->P * 4);
     return 0;
 }
 
@@ -572,24 +657,38 @@ int cs_bin_points(const cs_problem* pb, const float* coords, const float* offset
     const long long hist_bytes = round256((long long)b.nbins * 4);
     const unsigned nchunks = (b.nbins + cs::BIN_SCAN_CHUNK - 1) / cs::BIN_SCAN_CHUNK;
     const long long tot_bytes = round256(((long long)b.nbins / cs::BIN_SCAN_CHUNK + 1) * 4);
-    if (workspace_bytes < hist_bytes + tot_bytes + round256((long long)pb->P * 4))
+    const long long pt_bytes = round256((long long)pb->P * 4);
+    if (workspace_bytes < hist_bytes + tot_bytes + 2 * pt_bytes)
         return fail(CS_EINVAL, "cs_bin_points: workspace too small (see cs_bin_workspace_bytes)");
     b.coords = coords; b.offset = offset;
     unsigned* hist = reinterpret_cast<unsigned*>(workspace);
     unsigned* totals = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes);
     unsigned* rank = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes + tot_bytes);
+    unsigned* keys = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + hist_bytes + tot_bytes + pt_bytes);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)b.nbins * 4, s);
     if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points memset");
     long long blocks = (pb->P + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    cs::cs_bin_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, rank);
+    cs::cs_bin_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, keys, rank);
     cs::cs_bin_scan_chunk_kernel<<<nchunks, 1024, 0, s>>>(hist, b.nbins, totals);
     cs::cs_bin_scan_totals_kernel<<<1, 1024, 0, s>>>(totals, nchunks);
-    cs::cs_bin_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(b, hist, totals, rank, sorted, perm);
+    // destination windows of 2^23 points (64-96 MB: they stay in L2 while they fill up)
+    const long long window = 1ll << 23;
+    const int vec2 = ((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(sorted)) & 7u) == 0;
+    int sweeps = 0;
+    for (long long lo = 0; lo < pb->P; lo += window, ++sweeps) {
+        const unsigned hi = (unsigned)((lo + window < pb->P) ? lo + window : pb->P);
+        if (pb->dim == 2)
+            cs::cs_bin_scatter_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(coords, pb->P, vec2, hist, totals, keys, rank,
+                                                                         sweeps == 0 ? 1 : 0, (unsigned)lo, hi, sorted, perm);
+        else
+            cs::cs_bin_scatter_kernel<3><<<(unsigned)blocks, 256, 0, s>>>(coords, pb->P, 0, hist, totals, keys, rank,
+                                                                         sweeps == 0 ? 1 : 0, (unsigned)lo, hi, sorted, perm);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "cs_bin_points launch");
-    g_launches.fetch_add(4, std::memory_order_relaxed);
+    g_launches.fetch_add(3 + sweeps, std::memory_order_relaxed);
     return 0;
 }
 
@@ -717,6 +816,8 @@ int cs_peer_allreduce_from_channel_last(int32_t world, int32_t rank, const float
         }
     }
     p.small_out = small_out; p.small_n = small_n;
+    p.vec4 = 1;
+    for (int r = 0; r < world; ++r) if (!aligned16(acc_ptrs[r])) p.vec4 = 0;
     p.world = world; p.rank = rank; p.N = N; p.C = C; p.T = T;
     p.tiles_x = (T + 31) / 32; p.tiles_y = (C + 31) / 32;
     p.total_tiles = (long long)N * p.tiles_y * p.tiles_x;
@@ -727,6 +828,50 @@ int cs_peer_allreduce_from_channel_last(int32_t world, int32_t rank, const float
     cs_peer_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "peer reduce launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+
+int cs_peer_allreduce(int32_t world, int32_t rank, const float* const* acc_ptrs, float* const* out_ptrs, int64_t n,
+                      const float* acc_multicast, float* out_multicast, const float* const* small_ptrs,
+                      float* small_out, int32_t small_n, void* stream) {
+    if (world < 1 || world > CS_MAX_PEERS) return fail(CS_EUNSUPPORTED, "world must be 1..%d, got %d", CS_MAX_PEERS, world);
+    if (rank < 0 || rank >= world) return fail(CS_EINVAL, "bad rank %d of %d", rank, world);
+    if (n < 0 || small_n < 0) return fail(CS_EINVAL, "negative size");
+    if (n % 4 != 0) return fail(CS_EINVAL, "cs_peer_allreduce: n must be a multiple of 4 floats, got %lld", (long long)n);
+    if (!acc_ptrs || !out_ptrs) return fail(CS_EINVAL, "NULL pointer table");
+    if (small_n > 0 && (!small_ptrs || !small_out)) return fail(CS_EINVAL, "small vector given without pointers");
+    if ((acc_multicast == nullptr) != (out_multicast == nullptr))
+        return fail(CS_EINVAL, "cs_peer_allreduce: give both multicast addresses or neither");
+    PeerFlatParams p;
+    memset(&p, 0, sizeof(p));
+    for (int r = 0; r < world; ++r) {
+        if (!acc_ptrs[r] || !out_ptrs[r]) return fail(CS_EINVAL, "NULL peer buffer for rank %d", r);
+        if (!aligned16(acc_ptrs[r]) || !aligned16(out_ptrs[r])) return fail(CS_EINVAL, "peer buffers must be 16-byte aligned");
+        p.acc[r] = acc_ptrs[r]; p.out[r] = out_ptrs[r];
+        if (small_n > 0) {
+            if (!small_ptrs[r]) return fail(CS_EINVAL, "NULL small buffer for rank %d", r);
+            p.small_in[r] = small_ptrs[r];
+        }
+    }
+    if (acc_multicast && (!aligned16(acc_multicast) || !aligned16(out_multicast)))
+        return fail(CS_EINVAL, "multicast addresses must be 16-byte aligned");
+    p.acc_mc = acc_multicast; p.out_mc = out_multicast;
+    p.small_out = small_out; p.small_n = small_n;
+    p.world = world; p.rank = rank; p.n4 = n / 4;
+    const long long per = (p.n4 + world - 1) / world;
+    p.begin4 = per * rank < p.n4 ? per * rank : p.n4;
+    p.end4 = p.begin4 + per < p.n4 ? p.begin4 + per : p.n4;
+    long long blocks = (p.end4 - p.begin4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks += (small_n > 0 ? 1 : 0);
+    if (blocks < 1) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (acc_multicast) cs_peer_flat_reduce_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(p);
+    else cs_peer_flat_reduce_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "peer all-reduce launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }

@@ -92,12 +92,27 @@ __device__ __forceinline__ unsigned bin_key(const float* gp, const BinParams& p)
     return (key << (3 * p.sub)) | (unsigned)((((sz << p.sub) | sy) << p.sub) | sx);
 }
 
+// Both sweeps over the points keep BIN_ILP independent points in flight per thread: with one load per thread
+// the resident threads hold ~1 MB in flight and the sweeps ran at 1 TB/s (latency-bound).
+constexpr int BIN_ILP = 4;
+
 static __global__ void __launch_bounds__(256) cs_bin_count_kernel(const BinParams p, unsigned* __restrict__ hist,
+                                                                  unsigned* __restrict__ keys,
                                                                   unsigned* __restrict__ rank) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P;
-         i += (long long)gridDim.x * blockDim.x) {
-        const unsigned key = bin_key(p.coords + i * p.dim, p);
-        rank[i] = atomicAdd(hist + key, 1u);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.P; i0 += BIN_ILP * stride) {
+        unsigned key[BIN_ILP];
+#pragma unroll
+        for (int u = 0; u < BIN_ILP; ++u) {
+            const long long i = i0 + u * stride;
+            key[u] = (i < p.P) ? bin_key(p.coords + i * p.dim, p) : 0u;
+        }
+        unsigned r[BIN_ILP];
+#pragma unroll
+        for (int u = 0; u < BIN_ILP; ++u) r[u] = (i0 + u * stride < p.P) ? atomicAdd(hist + key[u], 1u) : 0u;
+#pragma unroll
+        for (int u = 0; u < BIN_ILP; ++u)
+            if (i0 + u * stride < p.P) { keys[i0 + u * stride] = key[u]; rank[i0 + u * stride] = r[u]; }
     }
 }
 
@@ -147,18 +162,55 @@ static __global__ void __launch_bounds__(1024) cs_bin_scan_totals_kernel(unsigne
     }
 }
 
-static __global__ void __launch_bounds__(256) cs_bin_scatter_kernel(const BinParams p, const unsigned* __restrict__ offs,
+// The destinations are random: a single sweep writes 4*dim bytes into random 32-byte sectors of a buffer larger
+// than L2 and every sector is read-modified-written in DRAM (1.19 ms for 2^25 points).  The sweep is therefore
+// repeated per destination window [lo, hi) small enough to stay in L2, where the partial sectors merge before
+// they are written back.  The first sweep turns (key, rank) into the final position and stores it over the rank,
+// so that the later sweeps read 4 bytes per point and the coordinates only of the points they place.
+template <int DIM>
+static __global__ void __launch_bounds__(256) cs_bin_scatter_kernel(const float* __restrict__ coords, long long P, int vec2,
+                                                                    const unsigned* __restrict__ offs,
                                                                     const unsigned* __restrict__ totals,
-                                                                    const unsigned* __restrict__ rank,
+                                                                    const unsigned* __restrict__ keys,
+                                                                    unsigned* __restrict__ rank, int first,
+                                                                    unsigned lo, unsigned hi,
                                                                     float* __restrict__ sorted, int* __restrict__ perm) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P;
-         i += (long long)gridDim.x * blockDim.x) {
-        const float* gp = p.coords + i * p.dim;
-        const unsigned key = bin_key(gp, p);
-        const long long pos = (long long)__ldg(offs + key) + __ldg(totals + key / BIN_SCAN_CHUNK) + __ldg(rank + i);
-        float* dst = sorted + pos * p.dim;
-        for (int a = 0; a < p.dim; ++a) dst[a] = __ldg(gp + a);
-        if (perm) perm[pos] = (int)i;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < P; i0 += BIN_ILP * stride) {
+        unsigned pos[BIN_ILP];
+        if (first) {
+            unsigned key[BIN_ILP], r[BIN_ILP];
+#pragma unroll
+            for (int u = 0; u < BIN_ILP; ++u) {
+                const long long i = i0 + u * stride;
+                key[u] = (i < P) ? __ldcs(keys + i) : 0u;
+                r[u] = (i < P) ? rank[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < BIN_ILP; ++u) {
+                pos[u] = __ldg(offs + key[u]) + __ldg(totals + key[u] / BIN_SCAN_CHUNK) + r[u];
+                if (i0 + u * stride < P) rank[i0 + u * stride] = pos[u];
+                else pos[u] = 0xffffffffu;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < BIN_ILP; ++u) pos[u] = (i0 + u * stride < P) ? __ldcs(rank + i0 + u * stride) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < BIN_ILP; ++u) {
+            if (pos[u] >= lo && pos[u] < hi) {
+                const unsigned i = (unsigned)(i0 + u * stride);
+                if (DIM == 2 && vec2) {
+                    reinterpret_cast<float2*>(sorted)[pos[u]] = __ldg(reinterpret_cast<const float2*>(coords) + i);
+                } else {
+                    const float* gp = coords + (size_t)i * DIM;
+                    float* dst = sorted + (size_t)pos[u] * DIM;
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) dst[a] = __ldg(gp + a);
+                }
+                if (perm) perm[pos[u]] = (int)i;
+            }
+        }
     }
 }
 
@@ -435,12 +487,15 @@ cs_pde_fused_kernel(const FusedParams p) {
     long long tile_end = tile_begin + p.tiles_per_warp;
     if (tile_end > p.num_ptiles) tile_end = p.num_ptiles;
 
+    // phase 1 runs one (cell, point) per lane: lane -> point (u * 32 + lane) % PTS; when a tile has fewer than 32
+    // points (3D: 16) the lanes beyond PTS take the same points for the NEXT cell (CPL cells per round)
+    constexpr int CPL = (PTS < 32) ? 32 / PTS : 1;
     auto load_coords = [&](float (&g)[PPL][DIM], bool (&inr)[PPL], long long tile) {
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
-            const int i = u * 32 + lane;
+            const int i = (u * 32 + lane) % PTS;
             const long long pi = tile * PTS + i;
-            inr[u] = (i < PTS) && (pi < p.P);
+            inr[u] = (u * 32 + lane < PTS * CPL) && (pi < p.P);
 #pragma unroll
             for (int a = 0; a < DIM; ++a) g[u][a] = 0.f;
             if (inr[u]) {
@@ -469,13 +524,17 @@ cs_pde_fused_kernel(const FusedParams p) {
         // ---- phase 1: records of every cell for the PTS points of this tile, one point per lane
         __syncwarp();                                   // everyone is done reading the previous tile's records
 #pragma unroll 1
-        for (int n = 0; n < ncells; ++n) {
-            const float off = __ldg(p.offset + n);
-            const int pad_index = (int)((long long)(ncells - n) * p.T);
+        for (int n0 = 0; n0 < ncells; n0 += CPL) {
+            const int n = n0 + (CPL > 1 ? lane / PTS : 0);
+            if (n < ncells) {
+                const float off = __ldg(p.offset + n);
+                const int pad_index = (int)((long long)(ncells - n) * p.T);
 #pragma unroll
-            for (int u = 0; u < PPL; ++u) {
-                const int i = u * 32 + lane;
-                if (i < PTS) build_fused_record<DIM, PTS>(recw + n * REC1, i, gcur[u], icur[u], off, pad_index, p);
+                for (int u = 0; u < PPL; ++u) {
+                    const int i = (u * 32 + lane) % PTS;
+                    if (u * 32 + lane < PTS * CPL)
+                        build_fused_record<DIM, PTS>(recw + n * REC1, i, gcur[u], icur[u], off, pad_index, p);
+                }
             }
         }
         __syncwarp();                                   // records are visible
@@ -612,6 +671,8 @@ cs_pde_fused_kernel(const FusedParams p) {
                 gw2acc[k] += gw2;
             }
             // the finished point enters the register tile at the top; after PPQ rounds point t sits in slot t
+            // (registers cannot be indexed by t; a warp-uniform switch over the slot measured 3 % slower than
+            // these moves)
 #pragma unroll
             for (int jt = 0; jt < J; ++jt)
 #pragma unroll

@@ -48,13 +48,14 @@ class PointShardedStep:
     mean over *all* points."""
 
     def __init__(self, sampler, cells, head, residual="helmholtz", chunk=None, group=None, fused=None,
-                 peer_reduce=False):
+                 peer_reduce=False, peer_multicast=None):
         """fused: None = `sampler` is a drop-in operator driven through `chain.training_step`
         (nested autograd, the reference's call pattern); a dict of `jet.fused_pde_step` keyword
         arguments (kernel=..., multicell=...) = the fused jet path (`sampler` is ignored).
         peer_reduce (fused path only): sum the gradients over the ranks with the fused peer-memory
         kernel (`peer.PeerReducer`, NVLink symmetric memory) instead of NCCL; the loss returned by
-        `step` is then the loss over ALL ranks' points (`loss_is_global`)."""
+        `step` is then the loss over ALL ranks' points (`loss_is_global`).  peer_multicast: None = sum inside
+        the NVSwitch (multimem) when the symmetric allocations have a multicast address, False = peer loads."""
         self.sampler, self.cells, self.head = sampler, cells, head
         self.residual, self.chunk, self.group = residual, chunk, group
         self.fused = fused
@@ -73,7 +74,8 @@ class PointShardedStep:
                 # the one-pass step scatters into the W1-mixed cells: K hidden units per texel
                 from .fused import head_params, small_buffer_size
                 K = head_params(head, cells.shape[1])[0].shape[0]
-                self.reducer = PeerReducer(cells, small_buffer_size(cells.shape[1], K), group, channels=K, tail=K)
+                self.reducer = PeerReducer(cells, small_buffer_size(cells.shape[1], K), group, channels=K, tail=K,
+                                           transpose=False, multicast=peer_multicast)
             elif self.mode == "jets":
                 from .jet import head_buffer_size
                 self.reducer = PeerReducer(cells, head_buffer_size(cells.shape[1]), group)

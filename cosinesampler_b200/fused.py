@@ -113,6 +113,31 @@ def bin_points(cells, coords, offset=None, align_corners=True, multicell=True, w
     return (out, perm) if want_perm else out
 
 
+class _BinCache:
+    """Binned copies of coordinate tensors that are fed again and again (a PIXEL run keeps its collocation
+    points for many steps): keyed on the tensor's storage pointer, version counter and the binning geometry.
+    The cache keeps the ORIGINAL tensor alive, so its storage cannot be recycled under the same pointer."""
+
+    def __init__(self, size=2):
+        self.size, self.items = size, []
+
+    def get(self, key, coords):
+        for k, orig, binned in self.items:
+            if k == key and orig._version == key[1]:      # `orig` (or a view of the same storage) is alive
+                return binned
+        return None
+
+    def put(self, key, coords, binned):
+        self.items = [it for it in self.items if it[0] != key][-(self.size - 1):] if self.size > 1 else []
+        self.items.append((key, coords, binned))
+
+    def clear(self):
+        self.items = []
+
+
+bin_cache = _BinCache()
+
+
 def head_premix(cells, W1):
     """Vh [N*T + 1, K]: W1 applied to cells [N, C, *S] texel by texel, plus one zero texel that
     out-of-bounds corners read (cs_head_premix).  `Vh[:N*T].view(N, T, K)` is the mixed stack."""
@@ -156,9 +181,12 @@ class OnePassPdeStep:
     (and sub-texel quadrant) first."""
 
     def __init__(self, cells, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
-                 align_corners=True, kernel="cosine", multicell=True, bin=True, aggregate="auto"):
+                 align_corners=True, kernel="cosine", multicell=True, bin=True, aggregate="auto", cache_bins=False):
+        """cache_bins: remember the binned copy of every coordinate tensor passed to `add` (`fused.bin_cache`,
+        the last two tensors) and reuse it while the tensor object, its storage and its version are unchanged."""
         ops._check(cells, "input")
         self.dim = _geometry(cells)[0]
+        self.cache_bins = bool(cache_bins)
         if self.dim == 2 and not align_corners:
             raise NotImplementedError(
                 "2D with align_corners=False: the reference's 2D forward ignores the flag (cu2d:307-308) while its "
@@ -215,7 +243,16 @@ class OnePassPdeStep:
         dev = self.cells.device
         with torch.no_grad():
             if self.bin:
-                xy = bin_points(self.cells_d, xy, self.offset, self.align_corners, self.multicell)
+                key = None
+                if self.cache_bins:
+                    key = (xy.data_ptr(), xy._version, tuple(xy.shape), str(xy.device), tuple(self.cells.shape[2:]),
+                           N, bool(self.align_corners), bool(self.multicell), ops.get_index_mode())
+                    hit = bin_cache.get(key, xy)
+                binned = hit if key is not None and hit is not None else \
+                    bin_points(self.cells_d, xy, self.offset, self.align_corners, self.multicell)
+                if key is not None and hit is None:
+                    bin_cache.put(key, xy, binned)
+                xy = binned
             pb = _problem(self.cells_d, P, self.K, self.pm, self.align_corners, self.kn, self.multicell)
             _, b1, w2, b2 = self.params
             base = self.buf.data_ptr()
@@ -237,10 +274,10 @@ class OnePassPdeStep:
         W1 = self.params[0].detach()
         with torch.no_grad():
             if self.reducer is not None:
-                # sum over the ranks in one kernel over peer memory: gVh arrives hidden-first [N, K, T], the
-                # loss and the head gradients are those of ALL ranks
+                # sum over the ranks in one kernel over peer memory (in the NVSwitch when the allocations have a
+                # multicast address); the loss and the head gradients are those of ALL ranks
                 gvh, buf = self.reducer.reduce()
-                hidden_first = True
+                hidden_first = self.reducer.transposed
             else:
                 gvh, buf, hidden_first = self.acc, self.buf, False
             loss_sum, pgrads = small_buffer_views(buf, C, self.K)
@@ -259,10 +296,11 @@ class OnePassPdeStep:
 
 def one_pass_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
                       align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0,
-                      reducer=None, bin=True, aggregate="auto"):
+                      reducer=None, bin=True, aggregate="auto", cache_bins=False):
     """`OnePassPdeStep` over coords [P, dim] in chunks of `chunk` points: accumulates `cells.grad` and the
     head parameters' `.grad`, returns loss_scale * mean_p f^2 as a 0-dim tensor."""
-    step = OnePassPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell, bin, aggregate)
+    step = OnePassPdeStep(cells, head, residual, k2, padding_mode, align_corners, kernel, multicell, bin, aggregate,
+                          cache_bins)
     P = coords.shape[0]
     chunk = max(1, P if not chunk else min(chunk, P))
     step.begin(reducer, scale=loss_scale / P if P else 0.0)

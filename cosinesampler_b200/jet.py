@@ -467,7 +467,7 @@ def fused_mode(cells, head, align_corners=True):
 
 def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, padding_mode="zeros",
                    align_corners=True, kernel="cosine", multicell=True, chunk=None, loss_scale=1.0, reducer=None,
-                   mode="auto"):
+                   mode="auto", cache_bins=False):
     """One training step over coords [P, dim] in chunks of `chunk` points without nested autograd:
     accumulates `cells.grad` and the head parameters' `.grad`, returns loss_scale * mean_p f^2 as a
     0-dim tensor.  mode: 'auto' (see `fused_mode`), 'onepass', 'jets' or 'torch_head'.  Falling back to
@@ -487,7 +487,7 @@ def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, p
     if mode == "onepass":
         from . import fused
         return fused.one_pass_pde_step(cells, coords, head, residual, k2, padding_mode, align_corners, kernel,
-                                       multicell, chunk, loss_scale, reducer)
+                                       multicell, chunk, loss_scale, reducer, cache_bins=cache_bins)
     if mode == "torch_head":
         if reducer is not None:
             raise NotImplementedError("the peer-memory reduce needs a fused head")

@@ -219,6 +219,16 @@ int cs_peer_allreduce_from_channel_last(int32_t world, int32_t rank, const float
                                         const float *const *small_ptrs, float *small_out, int32_t small_n,
                                         void *stream);
 
+/* Layout-preserving variant for the one-pass step (its accumulator is consumed as it is by cs_head_postmix):
+ * out_r[i] = sum_r acc_r[i] for i < n (n a multiple of 4), every rank owning a contiguous slice.  With
+ * acc_multicast / out_multicast (the NVSwitch multicast addresses of the same symmetric allocations; both or
+ * neither) the sum is taken inside the switch: one multimem.ld_reduce.add.v4.f32 and one multimem.st.v4.f32 per
+ * 16 bytes; without them the owner loads the slice from every peer (16-byte loads, rank order) and stores it to
+ * every peer.  Same barrier contract and small vector as above. */
+int cs_peer_allreduce(int32_t world, int32_t rank, const float *const *acc_ptrs, float *const *out_ptrs, int64_t n,
+                      const float *acc_multicast, float *out_multicast, const float *const *small_ptrs,
+                      float *small_out, int32_t small_n, void *stream);
+
 /* Staging between the reference layout and the channel-last layout.
  * src [N, C, T] -> dst [N, T, C]   (T = D*H*W) */
 int cs_to_channel_last(const float *src, float *dst, int32_t N, int32_t C, int64_t T, void *stream);

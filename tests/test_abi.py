@@ -129,8 +129,8 @@ def test_one_pass_entry_points_validate_arguments_without_a_gpu():
     pb.align_corners, pb.multicell = 1, 1
     n = ctypes.c_int64(0)
     assert lib.cs_bin_workspace_bytes(ctypes.byref(pb), ctypes.byref(n)) == 0
-    # 65 points per texel: 16 sub-bins per texel -> 2^20 bins, one rank word per point
-    assert n.value >= 4 * (2 ** 20 + 2 ** 22)
+    # 65 points per texel: 16 sub-bins per texel -> 2^20 bins, a key and a rank word per point
+    assert n.value >= 4 * (2 ** 20 + 2 * 2 ** 22)
     pb.P = 2 ** 31
     assert lib.cs_bin_workspace_bytes(ctypes.byref(pb), ctypes.byref(n)) == -2
     pb.P = 64

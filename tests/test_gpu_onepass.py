@@ -238,3 +238,37 @@ def test_one_pass_rejects_what_it_does_not_implement(cuda):
     # an empty chunk is a no-op
     loss = fused.one_pass_pde_step(torch.nn.Parameter(cells), coords[:0], ok)
     assert float(loss) == 0.0
+
+
+def test_bin_cache_reuses_and_invalidates(cuda):
+    """cache_bins: the binned copy is reused while the coordinate tensor is unchanged and rebuilt after an
+    in-place modification (version counter) -- same results either way."""
+    from cosinesampler_b200 import fused
+    gen = torch.Generator().manual_seed(3)
+    cells0 = torch.rand(4, 16, 32, 32, generator=gen).to(cuda)
+    coords = (torch.rand(5000, 2, generator=gen) * 2 - 1).to(cuda)
+    head = make_head(16, seed=1).to(cuda)
+    fused.bin_cache.clear()
+
+    def run(cache):
+        cells = torch.nn.Parameter(cells0.clone())
+        for p in head.parameters():
+            p.grad = None
+        loss = fused.one_pass_pde_step(cells, coords, head, "helmholtz", cache_bins=cache)
+        return loss.detach().clone(), cells.grad.clone()
+    ref = run(False)
+    a = run(True)
+    assert len(fused.bin_cache.items) == 1
+    binned_first = fused.bin_cache.items[0][2]
+    b = run(True)
+    assert fused.bin_cache.items[0][2] is binned_first                  # reused
+    for x in (a, b):
+        assert_close_scaled(x[0], ref[0], "cached loss", rtol=1e-5)
+        assert_close_scaled(x[1], ref[1], "cached grad", rtol=1e-4, atol_scale=1e-5)
+    coords.mul_(0.5)                                                    # in place: version changes
+    ref2 = run(False)
+    c = run(True)
+    assert fused.bin_cache.items[-1][2] is not binned_first
+    assert_close_scaled(c[0], ref2[0], "invalidated loss", rtol=1e-5)
+    assert_close_scaled(c[1], ref2[1], "invalidated grad", rtol=1e-4, atol_scale=1e-5)
+    fused.bin_cache.clear()

@@ -45,3 +45,34 @@ def test_peer_reduce_single_device(cuda, world, shape):
     # same result as the single-rank path: sum, then cs_from_channel_last
     one = ops.from_channel_last(torch.stack(accs).sum(0), (N, C, T))
     assert_close_scaled(outs[0], one, "vs from_channel_last", rtol=1e-6, atol_scale=1e-6)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_flat_peer_allreduce_single_device(cuda, world):
+    """cs_peer_allreduce (layout-preserving, 16-byte peer loads; the multimem path needs NVSwitch multicast
+    objects and is exercised by the multi-GPU bench) with the ranks emulated as buffers on one device."""
+    from cosinesampler_b200 import _lib, ops
+    gen = torch.Generator().manual_seed(world)
+    for n in (4, 1000, 4 * 16 * 257 * 4):
+        accs = [torch.randn(n, generator=gen).to(cuda) for _ in range(world)]
+        outs = [torch.full((n,), float("nan"), device=cuda) for _ in range(world)]
+        smalls = [torch.randn(290, generator=gen).to(cuda) for _ in range(world)]
+        small_outs = [torch.zeros(290, device=cuda) for _ in range(world)]
+        arr = ctypes.c_void_p * 8
+        acc_ptrs, out_ptrs = arr(*[a.data_ptr() for a in accs]), arr(*[o.data_ptr() for o in outs])
+        small_ptrs = arr(*[s.data_ptr() for s in smalls])
+        lib = _lib.load()
+        for r in range(world):
+            rc = lib.cs_peer_allreduce(world, r, acc_ptrs, out_ptrs, n, None, None, small_ptrs,
+                                       small_outs[r].data_ptr(), 290, ops._cur_stream(cuda))
+            _lib.check(rc, "cs_peer_allreduce")
+        torch.cuda.synchronize()
+        ref = torch.stack([a.double() for a in accs]).sum(0)
+        for r in range(world):
+            assert_close_scaled(outs[r], ref, "flat world=%d n=%d rank=%d" % (world, n, r), rtol=1e-6, atol_scale=1e-6)
+            assert torch.equal(outs[r], outs[0])
+            assert_close_scaled(small_outs[r], torch.stack([s.double() for s in smalls]).sum(0), "flat small",
+                                rtol=1e-6, atol_scale=1e-6)
+    # argument validation
+    assert lib.cs_peer_allreduce(2, 0, acc_ptrs, out_ptrs, 6, None, None, None, None, 0, None) == -1
+    assert lib.cs_peer_allreduce(2, 0, acc_ptrs, out_ptrs, 8, accs[0].data_ptr(), None, None, None, 0, None) == -1

@@ -68,5 +68,7 @@ def test_step_matches_reference_cuda_op_at_baseline_size(cuda, name):
         what = "%s %s vs reference CUDA op: " % (name, mode)
         assert_close_scaled(res[mode][0], rl, what + "loss", rtol=1e-4)
         assert_close_scaled(res[mode][1], rg, what + "d loss / d cells", rtol=1e-4, atol_scale=2e-5, max_outlier_frac=1e-4)
+        # the head gradients are fp32 sums of 2^20 - 2^22 terms of both signs (gb2 is a single such sum): the two
+        # sides order them differently (torch reductions vs fp32 atomics), which is worth a few 1e-4
         for a, b in zip(res[mode][2], rh):
-            assert_close_scaled(a, b, what + "head grad", rtol=1e-4, atol_scale=2e-5)
+            assert_close_scaled(a, b, what + "head grad", rtol=5e-4, atol_scale=1e-4)

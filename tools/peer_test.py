@@ -25,11 +25,19 @@ def main():
     xy = (torch.rand(e - s, 2, generator=torch.Generator().manual_seed(100 + rank)) * 2 - 1).to(dev)
     res = {}
     steppers = {}
-    for mode in ("nccl", "peer"):
+    kinds = {}
+    # nccl: one-pass step + NCCL all-reduce;  peer: one-pass step + cs_peer_allreduce (multimem when the box has
+    # multicast objects);  peer_ld: the same with 16-byte peer loads;  jets_peer: the round-1 path with the
+    # transposing cs_peer_allreduce_from_channel_last
+    for mode in ("nccl", "peer", "peer_ld", "jets_peer"):
         cells = torch.nn.Parameter(cells0.clone().to(dev))
         head = make_head(16, seed=0, device=dev)
-        st = dp.PointShardedStep(None, cells, head, residual="helmholtz", chunk=1 << 20,
-                                 fused=dict(kernel="cosine", multicell=True), peer_reduce=(mode == "peer"))
+        fk = dict(kernel="cosine", multicell=True)
+        if mode == "jets_peer":
+            fk["mode"] = "jets"
+        st = dp.PointShardedStep(None, cells, head, residual="helmholtz", chunk=1 << 22, fused=fk,
+                                 peer_reduce=(mode != "nccl"), peer_multicast=(False if mode == "peer_ld" else None))
+        kinds[mode] = st.reducer.kind if st.reducer is not None else "NCCL all-reduce"
         steppers[mode] = st
         st.zero_grad()
         loss = st.step(xy, total).detach().clone()
@@ -39,11 +47,12 @@ def main():
     torch.cuda.synchronize()
     ok = True
     msgs = []
-    for name, a, b in [("loss", res["peer"][0], res["nccl"][0]), ("cells.grad", res["peer"][1], res["nccl"][1])] + \
-            [("head%d" % i, a, b) for i, (a, b) in enumerate(zip(res["peer"][2], res["nccl"][2]))]:
-        err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
-        msgs.append("%s %.2e" % (name, err))
-        ok = ok and err < 2e-5
+    for mode in ("peer", "peer_ld", "jets_peer"):
+        for name, a, b in [("loss", res[mode][0], res["nccl"][0]), ("cells.grad", res[mode][1], res["nccl"][1])] + \
+                [("head%d" % i, a, b) for i, (a, b) in enumerate(zip(res[mode][2], res["nccl"][2]))]:
+            err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+            msgs.append("%s %s %.2e" % (mode, name, err))
+            ok = ok and err < (2e-4 if name.startswith("head") else 2e-5)
     # every rank must hold the same bits after the peer reduce
     gsum = res["peer"][1].double().sum().reshape(1)
     lst = [torch.zeros_like(gsum) for _ in range(world)]
@@ -65,7 +74,7 @@ def main():
         times[mode] = float(ms)
     if rank == 0:
         print(json.dumps({"world": world, "points": total, "match": ok, "same_bits_on_all_ranks": same,
-                          "rel_err": msgs, "ms_step_nccl": times["nccl"], "ms_step_peer": times["peer"]}), flush=True)
+                          "rel_err": msgs, "ms_step": times, "reducers": kinds}), flush=True)
     dist.destroy_process_group()
     if not (ok and same):
         sys.exit(1)
