@@ -14,6 +14,7 @@ EXPORTS = (
     "cs_version", "cs_last_error", "cs_launch_count",
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
+    "cs_forward_f64", "cs_backward_f64", "cs_backward_backward_f64", "cs_backward_backward_backward_f64",
     "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step", "cs_peer_allreduce_from_channel_last",
     "cs_peer_allreduce",
     "cs_bin_workspace_bytes", "cs_bin_points", "cs_head_premix", "cs_head_postmix", "cs_pde_fused_step",
@@ -81,6 +82,14 @@ def load():
     lib.cs_backward_backward.argtypes = [pp, vp, vp, vp, vp, Stream3, vp, vp, vp, vp, vp]
     lib.cs_backward_backward_backward.restype = ctypes.c_int
     lib.cs_backward_backward_backward.argtypes = [pp, vp, vp, Stream3, vp, vp, Stream3, vp, vp, vp, vp]
+    lib.cs_forward_f64.restype = ctypes.c_int
+    lib.cs_forward_f64.argtypes = [pp, vp, vp, vp, vp, vp]
+    lib.cs_backward_f64.restype = ctypes.c_int
+    lib.cs_backward_f64.argtypes = [pp, Stream3, vp, vp, vp, vp, vp, vp]
+    lib.cs_backward_backward_f64.restype = ctypes.c_int
+    lib.cs_backward_backward_f64.argtypes = [pp, vp, vp, vp, vp, Stream3, vp, vp, vp, vp, vp]
+    lib.cs_backward_backward_backward_f64.restype = ctypes.c_int
+    lib.cs_backward_backward_backward_f64.argtypes = [pp, vp, vp, Stream3, vp, vp, Stream3, vp, vp, vp, vp]
     lib.cs_jet_forward.restype = ctypes.c_int
     lib.cs_jet_forward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
     lib.cs_jet_backward.restype = ctypes.c_int

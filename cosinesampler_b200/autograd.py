@@ -159,6 +159,8 @@ def _engine_wants(ctx, idx):
 
 
 def _staged_of(offset, input):
+    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+        return None                      # the double-precision path reads the reference layout directly
     ops._check(input, "input")
     st = getattr(offset, "_cs_staged", None)
     if st is not None and st.matches(input):
@@ -286,8 +288,9 @@ def make_functions(dim):
         @staticmethod
         def forward(ctx, input, grid, padding_mode="zeros", align_corners=True, kernel="cosine",
                     multicell=True):
-            ops._check(input, "input")
-            ops._grid_view(grid)
+            if not (isinstance(input, torch.Tensor) and input.dtype == torch.float64):
+                ops._check(input, "input")
+                ops._grid_view(grid)
             offset = cell_offsets(input.shape[0], multicell, input.device)
             # a private view object per call: it carries the staging of `input`
             # to every later stage of this graph

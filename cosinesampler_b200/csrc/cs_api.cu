@@ -12,6 +12,7 @@
 #include "cs_jet.cuh"
 #include "cs_head.cuh"
 #include "cs_fused.cuh"
+#include "cs_scalar.cuh"
 
 namespace cs {
 // one function per (dim, field vector width, log2 lanes) variant, each in its own object file
@@ -421,7 +422,7 @@ int jet_run(const cs_problem* pb, int order, bool backward, const float* field_i
             const float* coords, const float* offset, float* jets_out, const float* jets_in, void* stream) {
     if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
     if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
-    if (order != 1 && order != 2) return fail(CS_EINVAL, "jet order must be 1 or 2, got %d", order);
+    if (order < 1 || order > 3) return fail(CS_EINVAL, "jet order must be 1, 2 or 3, got %d", order);
     if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
     if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
     if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
@@ -522,14 +523,49 @@ template <int K, bool KFIRST>
 cudaError_t postmix_launch(const float* gVh, const float* V, const float* W1, float* gInput, int accumulate,
                            float* gW1, int N, int C, long long T, cudaStream_t s) {
     auto kern = cs::cs_head_postmix_kernel<K, KFIRST>;
-    const size_t smem = (size_t)(C * K + cs::POSTMIX_TT * (K + 1) + C * cs::POSTMIX_TT) * sizeof(float);
+    const size_t smem = (size_t)((K + C) * cs::POSTMIX_TS + C * K) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long tpc = (T + cs::POSTMIX_TT - 1) / cs::POSTMIX_TT;
     const long long ntiles = tpc * N;
-    long long blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
+    long long blocks = ntiles < 148 * 4 ? ntiles : 148 * 4;     // few blocks: K*C atomics each at the end
     kern<<<(unsigned)blocks, cs::POSTMIX_TT, smem, s>>>(gVh, V, W1, gInput, accumulate, gW1, C, T, tpc, ntiles);
     return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------
+// Double-precision path (cs_scalar.cuh)
+// ---------------------------------------------------------------------------
+int scalar_setup(const cs_problem* pb, cs::ScalarParams& p, const double* grid, const float* offset) {
+    if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
+    if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
+    if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
+    if (pb->H < 1 || pb->W < 1 || pb->D < 1) return fail(CS_EINVAL, "cell extent must be >= 1");
+    if (pb->dim == 2 && pb->D != 1) return fail(CS_EINVAL, "D must be 1 when dim == 2");
+    if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
+    if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
+    if (pb->field_layout != CS_LAYOUT_CHANNEL_FIRST)
+        return fail(CS_EUNSUPPORTED, "the double-precision path works on the reference (channel-first) layout");
+    if (pb->N == 0 || pb->C == 0 || pb->P == 0) return CS_NOTHING_TO_DO;
+    if (!grid || !offset) return fail(CS_EINVAL, "grid/offset pointer is NULL");
+    const long long T = (long long)pb->D * pb->H * pb->W;
+    if (T >= (1ll << 31)) return fail(CS_EUNSUPPORTED, "a cell has %lld texels; the texel index is 32-bit", T);
+    memset(&p, 0, sizeof(p));
+    p.N = pb->N; p.C = pb->C; p.P = pb->P; p.T = T;
+    p.size[0] = pb->W; p.size[1] = pb->H; p.size[2] = pb->D;
+    p.tstride[0] = 1; p.tstride[1] = pb->W; p.tstride[2] = pb->W * pb->H;
+    p.grid = grid; p.grid_sn = pb->grid_stride_n; p.offset = offset;
+    p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel; p.multicell = pb->multicell;
+    return 0;
+}
+
+int scalar_run(const cs_problem* pb, const cs::ScalarParams& p, int stage, void* stream) {
+    cudaError_t e = (pb->dim == 2) ? cs::launch_scalar<2>(stage, p, (cudaStream_t)stream)
+                                   : cs::launch_scalar<3>(stage, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "double-precision stage kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }
 
 }  // namespace
@@ -599,6 +635,56 @@ int cs_backward_backward_backward(const cs_problem* pb, const float* input, cons
     p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
     if (has_x2) { p.x2 = gOutggOut.ptr; p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
     return run(pb, p, cs::ST_BBB, false, has_x2, stream);
+}
+
+int cs_forward_f64(const cs_problem* pb, const double* input, const double* grid, const float* offset, double* out,
+                   void* stream) {
+    cs::ScalarParams p;
+    if (int rc = scalar_setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!input || !out) return fail(CS_EINVAL, "cs_forward_f64: input/out is NULL");
+    p.V = input; p.y = out;
+    return scalar_run(pb, p, cs::ST_F, stream);
+}
+
+int cs_backward_f64(const cs_problem* pb, cs_stream_f64 gOut, const double* input, const double* grid,
+                    const float* offset, double* gInput, double* gGrid, void* stream) {
+    cs::ScalarParams p;
+    if (int rc = scalar_setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr) return fail(CS_EINVAL, "cs_backward_f64: gOut is NULL");
+    if (gGrid && !input) return fail(CS_EINVAL, "cs_backward_f64: gGrid needs input");
+    if (!gInput && !gGrid) return 0;
+    p.V = input; p.acc = gInput; p.ggrid = gGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    return scalar_run(pb, p, cs::ST_B, stream);
+}
+
+int cs_backward_backward_f64(const cs_problem* pb, const double* gOutInput, const double* gOutGrid,
+                             const double* input, const double* grid, cs_stream_f64 gOut, const float* offset,
+                             double* gInput, double* gGrid, double* ggOut, void* stream) {
+    cs::ScalarParams p;
+    if (int rc = scalar_setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr || !gOutGrid) return fail(CS_EINVAL, "cs_backward_backward_f64: gOut/gOutGrid is NULL");
+    if ((gGrid || ggOut) && !input) return fail(CS_EINVAL, "cs_backward_backward_f64: gGrid/ggOut need input");
+    if (!gInput && !gGrid && !ggOut) return 0;
+    p.V = input; p.U = gOutInput; p.acc = gInput; p.ggrid = gGrid; p.y = ggOut; p.gog = gOutGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    return scalar_run(pb, p, cs::ST_BB, stream);
+}
+
+int cs_backward_backward_backward_f64(const cs_problem* pb, const double* input, const double* grid,
+                                      cs_stream_f64 gOut, const double* gOutGrid, const double* gOutgGrid,
+                                      cs_stream_f64 gOutggOut, const float* offset, double* gInput, double* ggOut,
+                                      void* stream) {
+    cs::ScalarParams p;
+    if (int rc = scalar_setup(pb, p, grid, offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr || !gOutGrid || !gOutgGrid)
+        return fail(CS_EINVAL, "cs_backward_backward_backward_f64: gOut/gOutGrid/gOutgGrid is NULL");
+    if (ggOut && !input) return fail(CS_EINVAL, "cs_backward_backward_backward_f64: ggOut needs input");
+    if (!gInput && !ggOut) return 0;
+    p.V = input; p.acc = gInput; p.y = ggOut; p.gog = gOutGrid; p.gogg = gOutgGrid;
+    p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (gOutggOut.ptr && gInput) { p.x2 = gOutggOut.ptr; p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
+    return scalar_run(pb, p, cs::ST_BBB, stream);
 }
 
 int cs_jet_forward(const cs_problem* pb, int32_t order, const float* input, const float* coords,

@@ -255,8 +255,12 @@ __global__ void __launch_bounds__(256) cs_head_premix_kernel(const float* __rest
 }
 
 // gInput[n, c, t] (+)= sum_k W1[k, c] * gVh[n, t, k]      and      gW1[k, c] += sum_{n,t} gVh[n, t, k] * V[n, c, t]
-// gVh is channel-last [N,T,K] (KFIRST = false) or channel-first [N,K,T] (the output of the peer reduce).
+// gVh is channel-last [N,T,K] (KFIRST = false) or channel-first [N,K,T] (the output of the transposing peer reduce).
+// A block owns tiles of TT texels: one texel per thread for gInput (the tile of gVh and V is parked in shared
+// memory on the way), then one (k, c) pair per thread for the tile's share of gW1, four texels per 128-bit
+// shared-memory load; the pairs' sums stay in registers over all tiles of the block and leave as one atomic each.
 constexpr int POSTMIX_TT = 128;              // texels per block tile
+constexpr int POSTMIX_TS = POSTMIX_TT + 4;   // row stride in shared memory (floats): rows 4 banks apart
 template <int K, bool KFIRST>
 __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float* __restrict__ gVh,
                                                                      const float* __restrict__ V,
@@ -264,10 +268,11 @@ __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float
                                                                      float* __restrict__ gInput, int accumulate,
                                                                      float* __restrict__ gW1, int C, long long T,
                                                                      long long ntiles_per_cell, long long ntiles) {
-    extern __shared__ float sm[];
-    float* w1s = sm;                                  // [C][K]
-    float* gs = w1s + C * K;                          // [TT][K+1]
-    float* vs = gs + POSTMIX_TT * (K + 1);            // [C][TT]
+    extern __shared__ float4 sm4[];
+    float* sm = reinterpret_cast<float*>(sm4);
+    float* gs = sm;                                   // [K][TS]
+    float* vs = gs + K * POSTMIX_TS;                  // [C][TS]
+    float* w1s = vs + C * POSTMIX_TS;                 // [C][K]
     const int tid = threadIdx.x;
     for (int e = tid; e < K * C; e += POSTMIX_TT) w1s[(e % C) * K + (e / C)] = __ldg(W1 + e);
     const int npairs = K * C;
@@ -299,19 +304,20 @@ __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float
             for (int k = 0; k < K; ++k) g[k] = 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) gs[tid * (K + 1) + k] = g[k];
+        for (int k = 0; k < K; ++k) gs[k * POSTMIX_TS + tid] = g[k];
+        const float* vp = V + n * C * T + t;
+        float* op = gInput ? gInput + n * C * T + t : nullptr;
+#pragma unroll 4
         for (int c = 0; c < C; ++c) {
-            float v = 0.f;
-            if (ok) v = __ldg(V + (n * C + c) * T + t);
-            if (ok && gInput) {
+            const float v = ok ? __ldg(vp + (long long)c * T) : 0.f;
+            vs[c * POSTMIX_TS + tid] = v;
+            if (ok && op) {
                 float gi = 0.f;
                 const float* wr = w1s + c * K;
 #pragma unroll
                 for (int k = 0; k < K; ++k) gi = fmaf(wr[k], g[k], gi);
-                float* o = gInput + (n * C + c) * T + t;
-                if (accumulate) *o += gi; else *o = gi;
+                if (accumulate) op[(long long)c * T] += gi; else op[(long long)c * T] = gi;
             }
-            vs[c * POSTMIX_TT + tid] = v;
         }
         __syncthreads();
         if (gW1) {
@@ -319,11 +325,16 @@ __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float
             for (int i = 0; i < MAXPP; ++i) {
                 const int pr = tid + i * POSTMIX_TT;
                 if (pr < npairs) {
-                    const int k = pr % K, c = pr / K;
-                    float s = 0.f;
+                    const float4* gr = reinterpret_cast<const float4*>(gs + (pr % K) * POSTMIX_TS);
+                    const float4* vr = reinterpret_cast<const float4*>(vs + (pr / K) * POSTMIX_TS);
+                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-                    for (int tt = 0; tt < POSTMIX_TT; ++tt) s = fmaf(gs[tt * (K + 1) + k], vs[c * POSTMIX_TT + tt], s);
-                    wacc[i] += s;
+                    for (int t4 = 0; t4 < POSTMIX_TT / 4; ++t4) {
+                        const float4 a = gr[t4], b = vr[t4];
+                        s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1);
+                        s0 = fmaf(a.z, b.z, s0); s1 = fmaf(a.w, b.w, s1);
+                    }
+                    wacc[i] += s0 + s1;
                 }
             }
         }

@@ -48,10 +48,13 @@ struct JetParams {
     int pad, align, kernel, multicell, index_mode;
 };
 
+// ORDER 1: value + first derivatives; 2: + pure second derivatives; 3: + the mixed second derivatives
+// ((x,y) in 2D; (x,y), (x,z), (y,z) in 3D) -- what the reference's 3D double backward contracts (cu3d:836-856)
 template <int DIM, int ORDER> struct JetLayout {
     static constexpr int NCORN = 1 << DIM;
     static constexpr int CQ = NCORN / 4;
-    static constexpr int J = 1 + ORDER * DIM;
+    static constexpr int NMIX = (ORDER >= 3) ? DIM * (DIM - 1) / 2 : 0;
+    static constexpr int J = 1 + (ORDER >= 2 ? 2 : 1) * DIM + NMIX;
     static constexpr int FIELDS4 = 1 + J * CQ;     // float4 fields per point: header + J coefficient sets
 };
 
@@ -110,6 +113,15 @@ __device__ __forceinline__ void build_jet_record(float4* rec4, int i, const floa
                 coef[1 + a][c] = dw[a][b[a]] * wo[a];
                 if (ORDER >= 2) coef[1 + DIM + a][c] = ew[a][b[a]] * wo[a];
             }
+            if (ORDER >= 3) {
+                if (DIM == 2) {
+                    coef[(1 + 2 * DIM) % J][c] = dw[0][b[0]] * dw[1][b[1]];
+                } else {
+                    coef[(1 + 2 * DIM) % J][c] = dw[0][b[0]] * dw[1][b[1]] * w[DIM - 1][b[DIM - 1]];
+                    coef[(2 + 2 * DIM) % J][c] = dw[0][b[0]] * dw[DIM - 1][b[DIM - 1]] * w[1][b[1]];
+                    coef[(3 + 2 * DIM) % J][c] = dw[1][b[1]] * dw[DIM - 1][b[DIM - 1]] * w[0][b[0]];
+                }
+            }
         }
     }
     rec4[i] = make_float4(__int_as_float(base), __int_as_float(mask), 0.f, 0.f);
@@ -162,7 +174,7 @@ __device__ __forceinline__ void build_jet_axis_record(float4* rec4, int i, const
 
 // One channel of one (x, y) slab of corners: v00 = (x low, y low), v10 = (x high, y low), v01, v11;
 // ax, ay = (w0, w1, d, e) of the two axes.  dW = (-d, +d), d2W = (+e, -e).
-struct SlabJet { float A, X, XX, Y, YY; };
+struct SlabJet { float A, X, XX, Y, YY, XY; };
 __device__ __forceinline__ SlabJet slab_contract(float v00, float v10, float v01, float v11, const float4& ax,
                                                  const float4& ay) {
     const float a0 = fmaf(v10, ax.y, v00 * ax.x);
@@ -175,6 +187,7 @@ __device__ __forceinline__ SlabJet slab_contract(float v00, float v10, float v01
     const float da = a1 - a0;
     s.Y = da * ay.z;
     s.YY = -da * ay.w;
+    s.XY = ax.z * ay.z * (d1 - d0);
     return s;
 }
 
@@ -427,7 +440,8 @@ cs_jet_fwd_kernel(const JetParams p) {
                         acc[0][t][k] += sj.A;
                         acc[1][t][k] += sj.X;
                         acc[2][t][k] += sj.Y;
-                        if (ORDER >= 2) { acc[3][t][k] += sj.XX; acc[4][t][k] += sj.YY; }
+                        if (ORDER >= 2) { acc[3 % J][t][k] += sj.XX; acc[4 % J][t][k] += sj.YY; }
+                        if (ORDER >= 3) acc[5 % J][t][k] += sj.XY;
                     }
                 } else {
                     const float4 az = rec[(DIM == 3 ? 3 : 2) * PTS + ri];
@@ -449,6 +463,11 @@ cs_jet_fwd_kernel(const JetParams p) {
                             acc[1 + DIM][t][k] += fmaf(hi.XX, az.y, lo.XX * az.x);
                             acc[2 + DIM][t][k] += fmaf(hi.YY, az.y, lo.YY * az.x);
                             acc[2 * DIM][t][k] += (lo.A - hi.A) * az.w;
+                        }
+                        if (ORDER >= 3) {
+                            acc[(1 + 2 * DIM) % J][t][k] += fmaf(hi.XY, az.y, lo.XY * az.x);
+                            acc[(2 + 2 * DIM) % J][t][k] += (hi.X - lo.X) * az.z;
+                            acc[(3 + 2 * DIM) % J][t][k] += (hi.Y - lo.Y) * az.z;
                         }
                     }
                 }
@@ -651,6 +670,8 @@ cudaError_t launch_jet_variant(int order, bool backward, JetParams& p, cudaStrea
     constexpr int PPQ = JetPPQ<DIM>::value;
     constexpr int PTS = PPQ * (32 >> LSHIFT);
     p.num_ptiles = (p.P + PTS - 1) / PTS;
+    if (order == 3)
+        return backward ? launch_jet_one<DIM, LSHIFT, 3, PPQ, true>(p, s) : launch_jet_one<DIM, LSHIFT, 3, PPQ, false>(p, s);
     if (order == 2)
         return backward ? launch_jet_one<DIM, LSHIFT, 2, PPQ, true>(p, s) : launch_jet_one<DIM, LSHIFT, 2, PPQ, false>(p, s);
     return backward ? launch_jet_one<DIM, LSHIFT, 1, PPQ, true>(p, s) : launch_jet_one<DIM, LSHIFT, 1, PPQ, false>(p, s);

@@ -39,8 +39,8 @@ SUPPORTED_CHANNELS = (4, 8, 16, 32)
 def _check_args(input, coords, order):
     ops._check(input, "input")
     ops._check(coords, "coords")
-    if order not in (1, 2):
-        raise ValueError("jet order must be 1 or 2, got %r" % (order,))
+    if order not in (1, 2, 3):
+        raise ValueError("jet order must be 1, 2 or 3 (2 + mixed second derivatives), got %r" % (order,))
     if coords.dim() != 2 or coords.shape[1] not in (2, 3):
         raise RuntimeError("coords must be [P, dim] with dim 2 or 3, got %s" % (tuple(coords.shape),))
     dim = coords.shape[1]
@@ -60,20 +60,27 @@ def _problem(input, coords, padding_mode, align_corners, kernel, multicell):
                         _lib.LAYOUT_CHANNEL_LAST, 0)
 
 
+def jet_count(dim, order):
+    """Number of jets: value + dim first derivatives + (order >= 2) dim pure second derivatives + (order == 3)
+    the dim(dim-1)/2 mixed ones, (x,y) in 2D and (x,y), (x,z), (y,z) in 3D -- what the reference's 3D double
+    backward contracts (cu3d:836-856); its 2D kernels leave the mixed term out (cu2d:675-678)."""
+    return 1 + min(order, 2) * dim + (dim * (dim - 1) // 2 if order >= 3 else 0)
+
+
 def jet_bytes(dim, N, C, P, T, order):
     """Algorithmic bytes of one jet pass (forward or backward): coordinates + the jets + one field."""
-    return 4 * (P * (dim + (1 + order * dim) * C) + N * C * T)
+    return 4 * (P * (dim + jet_count(dim, order) * C) + N * C * T)
 
 
 def jet_forward(input, coords, offset, padding_mode, align_corners, kernel, multicell, order=2, staged=None):
-    """jets [1 + order*dim, C, P] (cs_jet_forward).  `staged`: a channel-last copy of `input`
+    """jets [jet_count(dim, order), C, P] (cs_jet_forward).  `staged`: a channel-last copy of `input`
     (ops.stage) to reuse."""
     dim = _check_args(input, coords, order)
     ops._check(offset, "offset")
     field, layout = ops._field(input, staged)
     N, C = input.shape[:2]
     P = coords.shape[0]
-    jets = torch.empty((1 + order * dim, C, P), dtype=input.dtype, device=input.device)
+    jets = torch.empty((jet_count(dim, order), C, P), dtype=input.dtype, device=input.device)
     pb = _problem(input, coords, padding_mode, align_corners, kernel, multicell)
     nbytes = jet_bytes(dim, N, C, P, input[0, 0].numel() if N and C else 0, order)
     with ops._on_device(input.device), ops._timed("JET%dd[fwd]" % dim, nbytes, input.device):
@@ -92,8 +99,8 @@ def jet_backward_into(acc, gJets, input, coords, offset, padding_mode, align_cor
     ops._check(gJets, "gJets", contiguous=False)
     N, C = input.shape[:2]
     P = coords.shape[0]
-    if tuple(gJets.shape) != (1 + order * dim, C, P):
-        raise RuntimeError("gJets must be %s, got %s" % ((1 + order * dim, C, P), tuple(gJets.shape)))
+    if tuple(gJets.shape) != (jet_count(dim, order), C, P):
+        raise RuntimeError("gJets must be %s, got %s" % ((jet_count(dim, order), C, P), tuple(gJets.shape)))
     gJets = gJets.contiguous()
     pb = _problem(input, coords, padding_mode, align_corners, kernel, multicell)
     nbytes = jet_bytes(dim, N, C, P, input[0, 0].numel() if N and C else 0, order)
@@ -164,14 +171,17 @@ def jet_mlp(head, jets, dim, order=2):
     """Propagate jets [J, C, P] of the head's input through `head`, an `nn.Sequential` of
     Linear / Tanh layers (the reference's test head, `test_2d.py:42-47`), and return
     (u, [u_a], [u_aa]) -- each [P, out_features] -- exactly what the nested
-    `autograd.grad(u, x)`, `autograd.grad(u_x, x)` calls of `test_2d.py:55-127` produce.
+    `autograd.grad(u, x)`, `autograd.grad(u_x, x)` calls of `test_2d.py:55-127` produce; with order 3
+    a fourth element {(a, b): u_ab} holds the mixed second derivatives (a < b).
     Plain torch ops in the jets' own feature-major layout ([features, P], no transposes):
     differentiable once more by autograd, which is all a training step needs."""
     J = jets.shape[0]
-    assert J == 1 + order * dim
+    assert J == jet_count(dim, order)
+    pairs = [(a, b) for a in range(dim) for b in range(a + 1, dim)] if order >= 3 else []
     val = jets[0]                                   # [F, P]
     d1 = jets[1:1 + dim]                            # [dim, F, P]
     d2 = jets[1 + dim:1 + 2 * dim] if order >= 2 else None
+    dm = jets[1 + 2 * dim:] if pairs else None      # [pairs, F, P]
     for layer in head:
         if isinstance(layer, torch.nn.Linear):
             w = layer.weight
@@ -181,11 +191,15 @@ def jet_mlp(head, jets, dim, order=2):
             d1 = torch.matmul(w, d1)
             if d2 is not None:
                 d2 = torch.matmul(w, d2)
+            if dm is not None:
+                dm = torch.matmul(w, dm)
         elif isinstance(layer, torch.nn.Tanh):
             t = torch.tanh(val)
             s1 = 1 - t * t                          # tanh'
             if d2 is not None:
                 s2 = -2 * t * s1                    # tanh''
+                if dm is not None:
+                    dm = torch.stack([s2 * d1[a] * d1[b] + s1 * dm[m] for m, (a, b) in enumerate(pairs)])
                 d2 = s2 * d1 * d1 + s1 * d2
             d1 = s1 * d1
             val = t
@@ -194,6 +208,8 @@ def jet_mlp(head, jets, dim, order=2):
     u = val.t()
     u_a = [d1[a].t() for a in range(dim)]
     u_aa = [d2[a].t() for a in range(dim)] if d2 is not None else None
+    if order >= 3:
+        return u, u_a, u_aa, {pr: dm[m].t() for m, pr in enumerate(pairs)}
     return u, u_a, u_aa
 
 
@@ -504,7 +520,7 @@ def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, p
     return step.finish()
 
 
-__all__ = ["fused_mode", "SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
+__all__ = ["jet_count", "fused_mode", "SamplerJet2d", "SamplerJet3d", "jet_forward", "jet_backward", "jet_backward_into", "jet_mlp",
            "jet_bytes", "pde_head_step", "pde_head_loss", "fused_pde_step", "FusedPdeStep", "jet_autograd_step",
            "head_is_fusable",
            "residual_coefficients"]

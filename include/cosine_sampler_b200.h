@@ -125,6 +125,29 @@ int cs_backward_backward_backward(const cs_problem *pb, const float *input, cons
                                   cs_stream gOutggOut, const float *offset, float *gInput,
                                   float *ggOut, void *stream);
 
+/* ---- Double precision -----------------------------------------------------------
+ * The reference dispatches double through AT_DISPATCH_FLOATING_TYPES_AND_HALF (cu2d:905,948,1009,1076) but feeds
+ * its float offset tensor (modules_2d.py:25) through TensorInfo<scalar_t> (cu2d:914), so that instantiation cannot
+ * run.  These four entry points are what the dispatch promises: the stages above on double tensors in the
+ * reference (channel-first) layout, offset still fp32, every nullable / zero-initialisation rule unchanged,
+ * all arithmetic in double.  A correctness path (one thread per (cell, point)); no throughput claim. */
+typedef struct cs_stream_f64 {
+    const double *ptr;
+    int64_t stride_n; /* elements */
+    int64_t stride_c; /* elements */
+} cs_stream_f64;
+int cs_forward_f64(const cs_problem *pb, const double *input, const double *grid, const float *offset,
+                   double *out, void *stream);
+int cs_backward_f64(const cs_problem *pb, cs_stream_f64 gOut, const double *input, const double *grid,
+                    const float *offset, double *gInput, double *gGrid, void *stream);
+int cs_backward_backward_f64(const cs_problem *pb, const double *gOutInput, const double *gOutGrid,
+                             const double *input, const double *grid, cs_stream_f64 gOut, const float *offset,
+                             double *gInput, double *gGrid, double *ggOut, void *stream);
+int cs_backward_backward_backward_f64(const cs_problem *pb, const double *input, const double *grid,
+                                      cs_stream_f64 gOut, const double *gOutGrid, const double *gOutgGrid,
+                                      cs_stream_f64 gOutggOut, const float *offset, double *gInput,
+                                      double *ggOut, void *stream);
+
 /* ---- Fused multi-cell jet operator (not in the reference; SURVEY section 8f ranks 1 + 2) ------------
  * One gather pass replaces the forward, first-backward (gGrid) and double-backward (gGrid) calls of
  * modules_2d.py:22-74 for a point set shared by all N cells (test_2d.py:36-38) and the caller's sum
@@ -132,7 +155,10 @@ int cs_backward_backward_backward(const cs_problem *pb, const float *input, cons
  *     jets[0]        [C,P] = sum_n sum_q input[n, corner q] * w_q             (cu2d:315-353)
  *     jets[1+a]      [C,P] = sum_n sum_q input[n, corner q] * dw_q/dg_a       (cu2d:476-503)
  *     jets[1+dim+a]  [C,P] = sum_n sum_q input[n, corner q] * d2w_q/dg_a^2    (cu2d:694-706; order 2)
- * a = 0..dim-1 in the order of grid[..., a].  jets is [1 + order*dim, C, P] contiguous, coords [P, dim].
+ *     jets[1+2*dim+m][C,P] = sum_n sum_q input[n, corner q] * d2w_q/dg_a dg_b    (cu3d:836-856; order 3: the
+ *                            mixed second derivatives, m over (x,y) in 2D and (x,y), (x,z), (y,z) in 3D)
+ * a = 0..dim-1 in the order of grid[..., a].  jets is [J, C, P] contiguous with J = 1 + dim (order 1),
+ * 1 + 2*dim (order 2) or 1 + 2*dim + dim*(dim-1)/2 (order 3); coords [P, dim].
  * pb->field_layout must be CS_LAYOUT_CHANNEL_LAST (input is [N, T, C]) and C in {4, 8, 16, 32};
  * pb->grid_stride_n, lanes, small_cell, grad_order are ignored; align_corners is honoured in 2D too. */
 int cs_jet_forward(const cs_problem *pb, int32_t order, const float *input, const float *coords,

@@ -293,12 +293,24 @@ def _jet_setup(input, coords, offset, pad, align, kernel, multicell, index_mode,
     return _Setup(input, grid, offset, pad, align, kernel, multicell, index_mode, compute_dtype)
 
 
+def jet_count(nd, order):
+    """Number of jets: value + nd first + (order >= 2) nd pure second + (order == 3) nd(nd-1)/2 mixed second
+    derivatives, in the order (x,y) in 2D and (x,y), (x,z), (y,z) in 3D."""
+    return 1 + min(order, 2) * nd + (nd * (nd - 1) // 2 if order >= 3 else 0)
+
+
+def mixed_pairs(nd):
+    return [(a, b) for a in range(nd) for b in range(a + 1, nd)]
+
+
 def jet_forward(input, coords, offset, order=2, pad=0, align=True, kernel=0, multicell=True,
                 index_mode=0, compute_dtype=torch.float64):
-    """jets [1 + order*dim, C, P]: value, d/dg_a, d2/dg_a^2 of sum_n sample(input[n], coords)."""
+    """jets [jet_count(dim, order), C, P]: value, d/dg_a, d2/dg_a^2 (and, order 3, d2/dg_a dg_b) of
+    sum_n sample(input[n], coords).  The mixed terms are what the reference's 3D double backward contracts
+    (cu3d:836-856); its 2D kernels leave them out (cu2d:675-678)."""
     s = _jet_setup(input, coords, offset, pad, align, kernel, multicell, index_mode, compute_dtype)
     nd = s.nd
-    jets = torch.zeros(1 + order * nd, s.C, s.P, dtype=s.dt)
+    jets = torch.zeros(jet_count(nd, order), s.C, s.P, dtype=s.dt)
     for bits, idx, inb in s.corners():
         V = s.gather(input, idx, inb)                                   # [N,C,P]
         jets[0] += (V * s.w(bits).view(s.N, 1, s.P)).sum(0)
@@ -306,6 +318,9 @@ def jet_forward(input, coords, offset, order=2, pad=0, align=True, kernel=0, mul
             jets[1 + a] += (V * s.d1(bits, a).view(s.N, 1, s.P)).sum(0)
             if order >= 2:
                 jets[1 + nd + a] += (V * s.d2(bits, a, a).view(s.N, 1, s.P)).sum(0)
+        if order >= 3:
+            for m, (a, b) in enumerate(mixed_pairs(nd)):
+                jets[1 + 2 * nd + m] += (V * s.d2(bits, a, b).view(s.N, 1, s.P)).sum(0)
     return jets
 
 
@@ -323,5 +338,8 @@ def jet_backward(gJets, input_shape, coords, offset, order=2, pad=0, align=True,
             coef = coef + g[1 + a].unsqueeze(0) * s.d1(bits, a).view(s.N, 1, s.P)
             if order >= 2:
                 coef = coef + g[1 + nd + a].unsqueeze(0) * s.d2(bits, a, a).view(s.N, 1, s.P)
+        if order >= 3:
+            for m, (a, b) in enumerate(mixed_pairs(nd)):
+                coef = coef + g[1 + 2 * nd + m].unsqueeze(0) * s.d2(bits, a, b).view(s.N, 1, s.P)
         s.scatter(gI, idx, inb, coef)
     return gI.reshape(input_shape)

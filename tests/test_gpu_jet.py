@@ -23,7 +23,7 @@ def _off(N, multicell):
     return cell_offsets(N, multicell, torch.device("cpu")).clone()
 
 
-@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("order", [1, 2, 3])
 @pytest.mark.parametrize("C", [4, 8, 16, 32])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_jet_kernels_match_oracle(cuda, dim, C, order):
@@ -35,7 +35,7 @@ def test_jet_kernels_match_oracle(cuda, dim, C, order):
     inp = torch.rand((N, C) + sizes, generator=gen)
     coords = torch.rand(P, dim, generator=gen) * 2.6 - 1.3          # some points out of range
     off = _off(N, True)
-    J = 1 + order * dim
+    J = jet.jet_count(dim, order)
     G = torch.randn(J, C, P, generator=gen)
     for kernel, pad, align in (("cosine", 0, True), ("smooth-step", 1, True), ("linear", 2, True),
                                ("cosine", 0, False)):
@@ -320,3 +320,51 @@ def test_fused_pde_step_falls_back_for_other_heads(cuda):
     assert_close_scaled(res["fused"][1], res["dropin"][1], "fallback cells.grad", rtol=1e-4, atol_scale=2e-5)
     for a, b in zip(res["fused"][2], res["dropin"][2]):
         assert_close_scaled(a, b, "fallback head grad", rtol=1e-4, atol_scale=2e-5)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_mixed_second_derivatives_match_nested_autograd(cuda, dim):
+    """order 3 = order 2 + the mixed second derivatives (cu3d:836-856): u_ab from SamplerJet + jet_mlp equals
+    nested autograd through the oracle sampler in fp64, and so do u, u_a, u_aa; the backward reaches the cells."""
+    from cosinesampler_b200 import jet
+    fn = grid_sample_2d if dim == 2 else grid_sample_3d
+    S = jet.SamplerJet2d if dim == 2 else jet.SamplerJet3d
+    gen = torch.Generator().manual_seed(60 + dim)
+    shape = (4, 8, 20, 20) if dim == 2 else (3, 8, 10, 10, 10)
+    P = 3000
+    cells0 = torch.rand(shape, generator=gen)
+    coords0 = safe_coords(P, dim, shape[2:][::-1], shape[0], True, gen).float()
+    head32 = make_head(shape[1], seed=5).to(cuda)
+    head64 = make_head(shape[1], seed=5, dtype=torch.float64)
+    cells = cells0.to(cuda).requires_grad_(True)
+    jets = S.apply(cells, coords0.to(cuda).contiguous(), "zeros", True, "cosine", True, 3)
+    assert jets.shape[0] == jet.jet_count(dim, 3)
+    u, u_a, u_aa, u_ab = jet.jet_mlp(head32, jets, dim, order=3)
+    # fp64 oracle: nested autograd, mixed terms included
+    c64 = cells0.double().requires_grad_(True)
+    cols = [coords0[:, a:a + 1].double().requires_grad_(True) for a in range(dim)]
+    grid = torch.cat(cols, -1).reshape((1,) * dim + (P, dim)).repeat((shape[0],) + (1,) * (dim + 1))
+    val = fn(c64, grid, step="cosine", offset=True)
+    ur = head64(val.sum(0).reshape(shape[1], -1).t())
+    g1 = [torch.autograd.grad(ur.sum(), cols[a], create_graph=True)[0] for a in range(dim)]
+    assert_close_scaled(u, ur, "u", rtol=1e-4, atol_scale=2e-5)
+    for a in range(dim):
+        assert_close_scaled(u_a[a], g1[a], "u_%d" % a, rtol=1e-4, atol_scale=2e-5)
+        gaa = torch.autograd.grad(g1[a].sum(), cols[a], retain_graph=True)[0]
+        assert_close_scaled(u_aa[a], gaa, "u_%d%d" % (a, a), rtol=1e-4, atol_scale=2e-5)
+    for (a, b), v in u_ab.items():
+        gab = torch.autograd.grad(g1[a].sum(), cols[b], retain_graph=True)[0]
+        assert_close_scaled(v, gab, "u_%d%d" % (a, b), rtol=1e-4, atol_scale=2e-5)
+    # a residual with a mixed term: its gradient w.r.t. the cells through the jets' backward
+    f = sum(u_aa) + 0.7 * sum(u_ab.values()) + u
+    loss = (f ** 2).mean()
+    loss.backward()
+    fr = ur
+    for a in range(dim):
+        fr = fr + torch.autograd.grad(g1[a].sum(), cols[a], create_graph=True)[0]
+        for b in range(a + 1, dim):
+            fr = fr + 0.7 * torch.autograd.grad(g1[a].sum(), cols[b], create_graph=True)[0]
+    lr = (fr ** 2).mean()
+    gr = torch.autograd.grad(lr, c64)[0]
+    assert_close_scaled(loss, lr, "mixed loss", rtol=1e-4)
+    assert_close_scaled(cells.grad, gr, "mixed d loss / d cells", rtol=1e-4, atol_scale=2e-5)

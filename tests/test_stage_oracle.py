@@ -173,3 +173,34 @@ def test_jet_oracle_matches_stage_oracles(dim, name, kcode, multicell):
     close((jets * G).sum(), (inp * gI).sum())
     # order 1 is a prefix of order 2
     close(so.jet_forward(inp, coords, off, order=1, **kw), jets[:1 + dim])
+
+
+@pytest.mark.parametrize("name,kcode", KERNELS)
+def test_mixed_jets_match_the_3d_double_backward(name, kcode):
+    """order 3: the mixed second derivatives are what the reference's 3D double backward contracts
+    (cu3d:836-856): BB's gGrid_b with gOutGrid hot on axis a is <z_ab, gOut> for b != a; order 2 is a prefix;
+    and the adjoint identity <jets(V), G> = <V, jet_backward(G)> holds with the mixed rows included."""
+    dim = 3
+    inp, grid, off, gen = _setup(dim, True, seed=5, C=4)
+    N, C = inp.shape[:2]
+    P = grid.shape[-2]
+    coords = grid[0].reshape(P, dim)
+    kw = dict(pad=0, align=True, kernel=kcode, multicell=True, index_mode=2)
+    jets = so.jet_forward(inp, coords, off, order=3, **kw)
+    assert jets.shape == (so.jet_count(dim, 3), C, P) == (10, C, P)
+    close = lambda a, b: torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-11)
+    close(jets[:1 + 2 * dim], so.jet_forward(inp, coords, off, order=2, **kw))
+    gOut = torch.randn(C, P, generator=gen, dtype=torch.float64)
+    gOutN = gOut.reshape((1, C) + (1,) * (dim - 1) + (P,)).repeat((N,) + (1,) * (dim + 1))
+    for m, (a, b) in enumerate(so.mixed_pairs(dim)):
+        hot = torch.zeros(grid.shape, dtype=torch.float64)
+        hot[..., a] = 1.0
+        _, gG2, _ = so.backward_backward(None, hot, inp, grid, gOutN, off, input_requires_grad=False, **kw)
+        close((jets[1 + 2 * dim + m] * gOut).sum(0), gG2.reshape(N, P, dim)[..., b].sum(0))
+    G = torch.randn(jets.shape, generator=gen, dtype=torch.float64)
+    gI = so.jet_backward(G, inp.shape, coords, off, order=3, **kw)
+    close((jets * G).sum(), (inp * gI).sum())
+    # 2D has one mixed jet
+    inp2, grid2, off2, _ = _setup(2, True, seed=6, C=4)
+    j2 = so.jet_forward(inp2, grid2[0].reshape(-1, 2), off2, order=3, **kw)
+    assert j2.shape[0] == so.jet_count(2, 3) == 6

@@ -20,8 +20,10 @@ N, C = shape[:2]
 gshape = (N, 1, P, 2) if dim == 2 else (N, 1, 1, P, 3)
 inp = torch.rand(shape, device=dev)
 grid = (torch.rand((1,) + gshape[1:], device=dev) * 2 - 1).repeat((N,) + (1,) * (len(gshape) - 1))
-gOut = torch.randn((N, C) + gshape[1:-1], device=dev)
-gOut2 = torch.randn((N, C) + gshape[1:-1], device=dev)
+# the chain hands the operator a gOut that is EXPANDED over the cells (PIXEL's `val.sum(0)`, stride 0): profile
+# the launches the bench really issues (round 1 profiled a dense gOut and over-counted the moved bytes)
+gOut = torch.randn((1, C) + gshape[1:-1], device=dev).expand((N, C) + gshape[1:-1])
+gOut2 = torch.randn((1, C) + gshape[1:-1], device=dev).expand((N, C) + gshape[1:-1])
 gOG = torch.randn(gshape, device=dev)
 gOgG = torch.randn(gshape, device=dev)
 off = cell_offsets(N, True, dev)

@@ -10,11 +10,16 @@ NAMES = {"cfg3": ["F2d", "B2d[G]", "B2d[I]", "BB2d[GO]", "BB2d[IO]", "BBB2d[IO+X
          "cfg4": ["F3d", "B3d[G]", "B3d[I]", "BB3d[GO]", "BB3d[IO]", "BBB3d[IO+X2]"],
          # tools/profile_fused.py: the three kernels of the fused jet step
          "fused_cfg3": ["JET2d[fwd]", "HEAD2d", "JET2d[bwd]"],
-         "fused_cfg4": ["JET3d[fwd]", "HEAD3d", "JET3d[bwd]"]}
+         "fused_cfg4": ["JET3d[fwd]", "HEAD3d", "JET3d[bwd]"],
+         # tools/profile_onepass.py: the one-pass kernel, 2^22 binned points per launch
+         "onepass_cfg3": ["ONEPASS2d"], "onepass_cfg4": ["ONEPASS3d"]}
+POINTS = {"onepass_cfg3": 2 ** 22, "onepass_cfg4": 2 ** 22}
 NOTE = {"cfg3": "cells [4,16,256,256], 2^20 points, cosine multicell",
         "cfg4": "cells [4,16,64,64,64], 2^22 points, smoothstep multicell",
         "fused_cfg3": "tools/profile_fused.py: cells [4,16,256,256], 2^20 points, cosine multicell",
-        "fused_cfg4": "tools/profile_fused.py: cells [4,16,64,64,64], 2^22 points, smoothstep multicell"}
+        "fused_cfg4": "tools/profile_fused.py: cells [4,16,64,64,64], 2^22 points, smoothstep multicell",
+        "onepass_cfg3": "tools/profile_onepass.py: cells [4,16,256,256], 2^22 binned points, cosine multicell",
+        "onepass_cfg4": "tools/profile_onepass.py: cells [4,16,64,64,64], 2^22 binned points, smoothstep multicell"}
 SCALE = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
 
@@ -44,8 +49,11 @@ def main(raw, out, cfg):
             "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "warp_instructions": val(r, "smsp__inst_executed.sum"),
         }
-    json.dump({"source": "ncu --set full --clock-control none, %s (%s); second launch of each kernel"
-                         % (cfg, NOTE[cfg]), "kernels": summary}, open(out, "w"), indent=1)
+    doc = {"source": "ncu --set full --clock-control none, %s (%s); second launch of each kernel" % (cfg, NOTE[cfg]),
+           "kernels": summary}
+    if cfg in POINTS:
+        doc["points_per_launch"] = POINTS[cfg]
+    json.dump(doc, open(out, "w"), indent=1)
     for k, v in summary.items():
         print("%-14s %8.1f us  dram %7.1f MB  L2->L1 %7.1f MB  l1tex %4.1f%% req %4.1f%% lts %4.1f%% dram %4.1f%% issue %4.1f%% regs %d"
               % (k, v["ncu_duration_us"], v["traffic_bytes"] / 1e6, v["l2_to_l1_read_bytes"] / 1e6, v["l1tex_throughput_pct"],
