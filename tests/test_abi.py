@@ -106,7 +106,7 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.cs_jet_forward(ctypes.byref(pb), 2, None, None, None, None, None) == -2
     assert b"C in" in lib.cs_last_error()
     pb.C = 8
-    assert lib.cs_jet_forward(ctypes.byref(pb), 3, None, None, None, None, None) == -1
+    assert lib.cs_jet_forward(ctypes.byref(pb), 4, None, None, None, None, None) == -1
     assert b"order" in lib.cs_last_error()
     pb.field_layout = _lib.LAYOUT_CHANNEL_FIRST
     assert lib.cs_jet_backward(ctypes.byref(pb), 2, None, None, None, None, None) == -2
