@@ -528,7 +528,7 @@ cudaError_t postmix_launch(const float* gVh, const float* V, const float* W1, fl
     if (e != cudaSuccess) return e;
     const long long tpc = (T + cs::POSTMIX_TT - 1) / cs::POSTMIX_TT;
     const long long ntiles = tpc * N;
-    long long blocks = ntiles < 148 * 4 ? ntiles : 148 * 4;     // few blocks: K*C atomics each at the end
+    long long blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
     kern<<<(unsigned)blocks, cs::POSTMIX_TT, smem, s>>>(gVh, V, W1, gInput, accumulate, gW1, C, T, tpc, ntiles);
     return cudaGetLastError();
 }
@@ -855,6 +855,9 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
     if (((long long)pb->N * T + 1) * (long long)K >= (1ll << 31))
         return fail(CS_EUNSUPPORTED, "the mixed cells have %lld elements; the texel index is 32-bit", ((long long)pb->N * T + 1) * K);
     if (pb->P >= (1ll << 33)) return fail(CS_EUNSUPPORTED, "too many points (%lld)", (long long)pb->P);
+    if (pb->N > cs::FUSED_MAX_CELLS)
+        return fail(CS_EUNSUPPORTED, "cs_pde_fused_step holds the records of all cells in shared memory: at most %d cells, got %d",
+                    cs::FUSED_MAX_CELLS, pb->N);
     cs::FusedParams p;
     memset(&p, 0, sizeof(p));
     p.N = pb->N; p.P = pb->P; p.T = T;

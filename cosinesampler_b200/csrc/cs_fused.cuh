@@ -456,14 +456,27 @@ __device__ __forceinline__ SlabOut slab_blend(float v00, float v10, float v01, f
 #ifndef CS_FUSED_BLOCKS
 #define CS_FUSED_BLOCKS 3
 #endif
+// Unrolling over the cells pays for the gather only (NC = 4: 6.68 -> 6.14 ms per 2^25 points, its loads are in
+// flight together).  Unrolling phase 1 and the scatter by 2 / 4 cells grows the code and LOSES: 6.34 / 7.30 ms
+// (profiles/README.md): the kernel lives at the edge of the instruction cache.
+#ifndef CS_FUSED_UNROLL_P1
+#define CS_FUSED_UNROLL_P1 1
+#endif
+#ifndef CS_FUSED_UNROLL_C
+#define CS_FUSED_UNROLL_C 1
+#endif
 constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_UNROLL_P1 = CS_FUSED_UNROLL_P1;
+constexpr int FUSED_UNROLL_C = CS_FUSED_UNROLL_C;
 constexpr int FUSED_MAX_CELLS = 32;      // the records of all cells of a tile live in shared memory
 
 // Code size matters here: three inlined phases unrolled over the points of a walker were 8000 SASS
 // instructions (128 KB) and the kernel stalled on instruction fetch.  Gather + head run one point at a time in
 // a real loop (the finished point is rotated into the register tile), phase 1 has one call site, and corners
 // need no validity predicates: ~1500 instructions.
-template <int DIM, int LSHIFT>
+// NC: number of cells when it is known at compile time (4: the PIXEL configurations; the gather loop over the
+// cells is then fully unrolled and all its loads are in flight together), 0 = run-time p.N.
+template <int DIM, int LSHIFT, int NC>
 __global__ void __launch_bounds__(FUSED_THREADS, CS_FUSED_BLOCKS)
 cs_pde_fused_kernel(const FusedParams p) {
     constexpr int NCORN = 1 << DIM;
@@ -483,7 +496,7 @@ cs_pde_fused_kernel(const FusedParams p) {
     const int wpb = blockDim.x >> 5;
     const int q = lane >> LSHIFT;
     const int j = lane & (L - 1);
-    const int ncells = p.N;
+    const int ncells = NC > 0 ? NC : p.N;
     float4* recw = smem4 + (size_t)warp * ncells * REC1;
 
     float b1k[4], w2k[4];
@@ -534,7 +547,7 @@ cs_pde_fused_kernel(const FusedParams p) {
 
         // ---- phase 1: records of every cell for the PTS points of this tile, one point per lane
         __syncwarp();                                   // everyone is done reading the previous tile's records
-#pragma unroll 1
+#pragma unroll (NC > 0 ? FUSED_UNROLL_P1 : 1)
         for (int n0 = 0; n0 < ncells; n0 += CPL) {
             const int n = n0 + (CPL > 1 ? lane / PTS : 0);
             if (n < ncells) {
@@ -569,7 +582,7 @@ cs_pde_fused_kernel(const FusedParams p) {
             for (int jt = 0; jt < J; ++jt)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) h[jt][k] = 0.f;
-#pragma unroll 2
+#pragma unroll (NC > 0 ? NC : 2)
             for (int n = 0; n < ncells; ++n) {
                 const float4* rec = recw + n * REC1;
                 const float* vsrc = p.Vh + (long long)n * p.T * K + 4 * j;
@@ -696,7 +709,7 @@ cs_pde_fused_kernel(const FusedParams p) {
 
         // ---- C: scatter d loss / d H_jt into gVh (separable adjoint: per corner  Wy u_x +- Wx beta), pre-reduced in
         // registers over runs of consecutive points of this walker with identical corners
-#pragma unroll 1
+#pragma unroll (NC > 0 ? FUSED_UNROLL_C : 1)
         for (int n = 0; n < ncells; ++n) {
             const float4* rec = recw + n * REC1;
             float* gcell = p.gVh + (long long)n * p.T * K + 4 * j;
@@ -828,7 +841,7 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     constexpr int PPQ = (DIM == 2) ? 4 : 2;
     constexpr int PTS = PPQ * NW;
     constexpr int REC1 = ((1 << DIM) / 4 + DIM) * PTS;
-    auto kern = cs_pde_fused_kernel<DIM, LSHIFT>;
+    auto kern = (p.N == 4) ? cs_pde_fused_kernel<DIM, LSHIFT, 4> : cs_pde_fused_kernel<DIM, LSHIFT, 0>;
     if (p.N > FUSED_MAX_CELLS) return cudaErrorInvalidConfiguration;
     const size_t per_warp = (size_t)p.N * REC1 * sizeof(float4);
     int wpb = FUSED_THREADS / 32;

@@ -33,6 +33,7 @@ from .jet import residual_coefficients, _add_grad
 
 HIDDEN_WIDTHS = (4, 8, 16, 32)
 MAX_CHANNELS = 64
+MAX_CELLS = 32          # the records of all cells of a tile of points live in shared memory
 
 
 def head_params(head, C):
@@ -186,6 +187,10 @@ class OnePassPdeStep:
         the last two tensors) and reuse it while the tensor object, its storage and its version are unchanged."""
         ops._check(cells, "input")
         self.dim = _geometry(cells)[0]
+        if cells.shape[0] > MAX_CELLS:
+            raise NotImplementedError("the one-pass step holds the records of all cells in shared memory: at most %d "
+                                      "cells, got %d (jet.fused_pde_step falls back to the jets path)"
+                                      % (MAX_CELLS, cells.shape[0]))
         self.cache_bins = bool(cache_bins)
         if self.dim == 2 and not align_corners:
             raise NotImplementedError(

@@ -474,7 +474,7 @@ def fused_mode(cells, head, align_corners=True):
     'torch_head' (`jet_autograd_step`: jet kernels + the head's chain rule in torch ops)."""
     from . import fused
     C = cells.shape[1]
-    if fused.head_is_fusable(head, C) and (cells.dim() == 5 or align_corners):
+    if fused.head_is_fusable(head, C) and (cells.dim() == 5 or align_corners) and cells.shape[0] <= fused.MAX_CELLS:
         return "onepass"
     if head_is_fusable(head, C) and C in SUPPORTED_CHANNELS:
         return "jets"

@@ -235,6 +235,11 @@ def test_one_pass_rejects_what_it_does_not_implement(cuda):
         fused.one_pass_pde_step(cells, coords, ok, align_corners=False)
     with pytest.raises(RuntimeError):
         fused.one_pass_pde_step(cells.cpu(), coords, ok)
+    many = torch.rand(40, 8, 8, 8, device=cuda)                      # more cells than the records have room for
+    with pytest.raises(NotImplementedError):
+        fused.one_pass_pde_step(many, coords, ok)
+    from cosinesampler_b200 import jet
+    assert jet.fused_mode(many, ok) == "jets" and jet.fused_mode(cells, ok) == "onepass"
     # an empty chunk is a no-op
     loss = fused.one_pass_pde_step(torch.nn.Parameter(cells), coords[:0], ok)
     assert float(loss) == 0.0
