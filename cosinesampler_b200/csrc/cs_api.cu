@@ -522,17 +522,26 @@ int premix_launch(const float* V, const float* W1, float* Vh, int C, long long T
 template <int K, bool KFIRST>
 cudaError_t postmix_launch(const float* gVh, const float* V, const float* W1, float* gInput, int accumulate,
                            float* gW1, int N, int C, long long T, cudaStream_t s) {
+    const long long tpc = (T + cs::POSTMIX_TT - 1) / cs::POSTMIX_TT;
+    const long long ntiles = tpc * N;
+    static const long long mult = [] { const char* e = getenv("CS_POSTMIX_BLOCKS"); return e ? atoll(e) : 4ll; }();
+    long long blocks = ntiles < 148 * mult ? ntiles : 148 * mult;
+    if (!KFIRST) {
+        // channel-last gVh: the software-pipelined kernel (two stages of [TT][K] + [C][TT] in shared memory)
+        auto kern = cs::cs_head_postmix_pipe_kernel<K>;
+        const size_t smem = (size_t)(2 * (cs::POSTMIX_TT * K + C * (cs::POSTMIX_TT + 4)) + C * K) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, cs::POSTMIX_TT, smem, s>>>(gVh, V, W1, gInput, accumulate, gW1, C, T, tpc, ntiles);
+        return cudaGetLastError();
+    }
     auto kern = cs::cs_head_postmix_kernel<K, KFIRST>;
     const size_t smem = (size_t)((K + C) * cs::POSTMIX_TS + C * K) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const long long tpc = (T + cs::POSTMIX_TT - 1) / cs::POSTMIX_TT;
-    const long long ntiles = tpc * N;
-    long long blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
     kern<<<(unsigned)blocks, cs::POSTMIX_TT, smem, s>>>(gVh, V, W1, gInput, accumulate, gW1, C, T, tpc, ntiles);
     return cudaGetLastError();
 }
-
 
 // ---------------------------------------------------------------------------
 // Double-precision path (cs_scalar.cuh)

@@ -349,6 +349,128 @@ __global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_kernel(const float
     }
 }
 
+// The same pass for channel-last gVh, software-pipelined: the tile after this one streams into the other half of
+// shared memory with cp.async while this one is consumed (the kernel above waits for its loads tile by tile:
+// 31 % occupancy, 11 long-scoreboard stalls per issue, 0.19 ms for the 64 MiB fields of config 4).
+template <int K>
+__global__ void __launch_bounds__(POSTMIX_TT) cs_head_postmix_pipe_kernel(const float* __restrict__ gVh,
+                                                                          const float* __restrict__ V,
+                                                                          const float* __restrict__ W1,
+                                                                          float* __restrict__ gInput, int accumulate,
+                                                                          float* __restrict__ gW1, int C, long long T,
+                                                                          long long ntiles_per_cell, long long ntiles) {
+    constexpr int TT = POSTMIX_TT;
+    extern __shared__ float4 sm4[];
+    float* sm = reinterpret_cast<float*>(sm4);
+    constexpr int VS = TT + 4;                        // row stride of v: rows 4 banks apart
+    const int tile_f = TT * K + C * VS;               // floats per stage: g [TT][K] then v [C][VS]
+    float* w1s = sm + 2 * tile_f;                     // [C][K]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < K * C; e += TT) w1s[(e % C) * K + (e / C)] = __ldg(W1 + e);
+    const int npairs4 = (K / 4) * C;                  // a work item = 4 hidden units x 1 channel x half of the texels
+    constexpr int MAXW = (MIX_MAXK / 4 * 64 * 2 + TT - 1) / TT;
+    float4 wacc[MAXW];
+#pragma unroll
+    for (int i = 0; i < MAXW; ++i) wacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto issue = [&](long long tile, int st) {
+        const long long n = tile / ntiles_per_cell;
+        const long long t0 = (tile - n * ntiles_per_cell) * TT;
+        float* gs = sm + st * tile_f;
+        float* vs = gs + TT * K;
+        const unsigned gsb = (unsigned)__cvta_generic_to_shared(gs);
+        const unsigned vsb = (unsigned)__cvta_generic_to_shared(vs);
+        // g: TT texels x K floats, contiguous in global memory (16-byte pieces; zero-filled past T)
+        const float* gsrc = gVh + (n * T + t0) * K;
+        for (int e = tid; e < TT * K / 4; e += TT) {
+            const bool ok = t0 + (4 * e) / K < T;
+            cp16z(gsb + e * 16, ok ? gsrc + 4 * e : gVh, ok);
+        }
+        // v: C rows of TT texels
+        const bool vec = (T % 4 == 0);
+        for (int e = tid; e < C * TT / 4; e += TT) {
+            const int c = e / (TT / 4), q4 = e - c * (TT / 4);
+            const long long t = t0 + 4 * q4;
+            const float* src = V + (n * C + c) * T + t;
+            const unsigned dst = vsb + (c * VS + 4 * q4) * 4;
+            if (vec) {
+                const bool ok = t < T;
+                cp16z(dst, ok ? src : V, ok);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cp4z(dst + 4 * i, (t + i < T) ? src + i : V, t + i < T);
+            }
+        }
+        cp_async_commit();
+    };
+
+    __syncthreads();
+    long long tile = blockIdx.x;
+    int st = 0;
+    if (tile < ntiles) issue(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x, st ^= 1) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) { issue(next, st ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const float* gs = sm + st * tile_f;
+        const float* vs = gs + TT * K;
+        const long long n = tile / ntiles_per_cell;
+        const long long t = (tile - n * ntiles_per_cell) * TT + tid;
+        if (gInput && t < T) {
+            float g[K];
+#pragma unroll
+            for (int k4 = 0; k4 < K / 4; ++k4) {
+                const float4 v = reinterpret_cast<const float4*>(gs + tid * K)[k4];
+                g[4 * k4] = v.x; g[4 * k4 + 1] = v.y; g[4 * k4 + 2] = v.z; g[4 * k4 + 3] = v.w;
+            }
+            float* op = gInput + n * C * T + t;
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) {
+                float gi = 0.f;
+                const float* wr = w1s + c * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) gi = fmaf(wr[k], g[k], gi);
+                if (accumulate) op[(long long)c * T] += gi; else op[(long long)c * T] = gi;
+            }
+        }
+        if (gW1) {
+#pragma unroll
+            for (int i = 0; i < MAXW; ++i) {
+                const int w = tid + i * TT;
+                if (w < 2 * npairs4) {
+                    const int half = w / npairs4, pr = w - half * npairs4;
+                    const int kq = pr % (K / 4), c = pr / (K / 4);
+                    const float* gp = gs + (half * (TT / 2)) * K + 4 * kq;
+                    const float* vp = vs + c * VS + half * (TT / 2);
+                    float4 a = wacc[i];
+#pragma unroll 8
+                    for (int tt = 0; tt < TT / 2; ++tt) {
+                        const float4 gq = *reinterpret_cast<const float4*>(gp + tt * K);
+                        const float v = vp[tt];
+                        a.x = fmaf(gq.x, v, a.x); a.y = fmaf(gq.y, v, a.y); a.z = fmaf(gq.z, v, a.z); a.w = fmaf(gq.w, v, a.w);
+                    }
+                    wacc[i] = a;
+                }
+            }
+        }
+        __syncthreads();                                // the stage is free for the tile after next
+    }
+    if (gW1) {
+#pragma unroll
+        for (int i = 0; i < MAXW; ++i) {
+            const int w = tid + i * TT;
+            if (w < 2 * npairs4) {
+                const int pr = w % npairs4;
+                const int kq = pr % (K / 4), c = pr / (K / 4);
+                atomicAdd(gW1 + (4 * kq + 0) * C + c, wacc[i].x);
+                atomicAdd(gW1 + (4 * kq + 1) * C + c, wacc[i].y);
+                atomicAdd(gW1 + (4 * kq + 2) * C + c, wacc[i].z);
+                atomicAdd(gW1 + (4 * kq + 3) * C + c, wacc[i].w);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // The fused step
 // ---------------------------------------------------------------------------------------------------------
