@@ -21,7 +21,7 @@ UNITS += [("cs_jet_inst.cu", "cs_jet_d%d_l%d.o" % (d, l), ["-DCS_DIM=%d" % d, "-
           for d in (2, 3) for l in (0, 1, 2, 3)]
 UNITS += [("cs_head_inst.cu", "cs_head.o", [])]
 UNITS += [("cs_fused_inst.cu", "cs_fused_d%d_l%d.o" % (d, l), ["-DCS_DIM=%d" % d, "-DCS_LSHIFT=%d" % l])
-          for d in (2, 3) for l in (0, 1, 2, 3)]
+          for d in (2, 3) for l in (0, 1, 2, 3, 4)]
 SOURCES = ["cs_api.cu", "cs_stage_inst.cu", "cs_jet_inst.cu", "cs_head_inst.cu", "cs_fused_inst.cu"]
 HEADERS = ["cs_engine.cuh", "cs_launch.cuh", "cs_jet.cuh", "cs_head.cuh", "cs_head_mma.cuh", "cs_fused.cuh", "cs_scalar.cuh", os.path.join("..", "..", "include", "cosine_sampler_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

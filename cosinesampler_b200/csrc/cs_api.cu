@@ -28,6 +28,7 @@ CS_DECLJ(launch_jet_d3_l0) CS_DECLJ(launch_jet_d3_l1) CS_DECLJ(launch_jet_d3_l2)
 cudaError_t launch_head_any(int dim, int C, const HeadParams& p, cudaStream_t s);
 #define CS_DECLF(name) cudaError_t name(FusedParams& p, cudaStream_t s);
 CS_DECLF(launch_fused_d2_l0) CS_DECLF(launch_fused_d2_l1) CS_DECLF(launch_fused_d2_l2) CS_DECLF(launch_fused_d2_l3)
+CS_DECLF(launch_fused_d2_l4) CS_DECLF(launch_fused_d3_l4)
 CS_DECLF(launch_fused_d3_l0) CS_DECLF(launch_fused_d3_l1) CS_DECLF(launch_fused_d3_l2) CS_DECLF(launch_fused_d3_l3)
 #undef CS_DECLF
 }  // namespace cs
@@ -789,7 +790,8 @@ int cs_bin_points(const cs_problem* pb, const float* coords, const float* offset
 
 static int mix_check(int32_t N, int32_t C, int64_t T, int32_t K) {
     if (N < 0 || C < 0 || T < 0) return fail(CS_EINVAL, "negative size");
-    if (!(K == 4 || K == 8 || K == 16 || K == 32)) return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16 or 32, got %d", K);
+    if (!(K == 4 || K == 8 || K == 16 || K == 32 || K == 64))
+        return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16, 32 or 64, got %d", K);
     if (C > 64) return fail(CS_EUNSUPPORTED, "the W1 mixes support at most 64 input channels, got %d", C);
     return 0;
 }
@@ -806,7 +808,8 @@ int cs_head_premix(int32_t N, int32_t C, int64_t T, int32_t K, const float* inpu
         case 4: premix_launch<4>(input, W1, Vh, C, T, NT, s); break;
         case 8: premix_launch<8>(input, W1, Vh, C, T, NT, s); break;
         case 16: premix_launch<16>(input, W1, Vh, C, T, NT, s); break;
-        default: premix_launch<32>(input, W1, Vh, C, T, NT, s); break;
+        case 32: premix_launch<32>(input, W1, Vh, C, T, NT, s); break;
+        default: premix_launch<64>(input, W1, Vh, C, T, NT, s); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "cs_head_premix launch");
@@ -830,7 +833,8 @@ int cs_head_postmix(int32_t N, int32_t C, int64_t T, int32_t K, const float* gVh
         case 4: CS_POSTMIX(4); break;
         case 8: CS_POSTMIX(8); break;
         case 16: CS_POSTMIX(16); break;
-        default: CS_POSTMIX(32); break;
+        case 32: CS_POSTMIX(32); break;
+        default: CS_POSTMIX(64); break;
     }
 #undef CS_POSTMIX
     if (e != cudaSuccess) return cuda_fail(e, "cs_head_postmix launch");
@@ -855,8 +859,8 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
     if (pb->field_layout != CS_LAYOUT_CHANNEL_LAST)
         return fail(CS_EUNSUPPORTED, "cs_pde_fused_step needs the channel-last mixed cells of cs_head_premix");
     const int K = pb->C;
-    if (!(K == 4 || K == 8 || K == 16 || K == 32))
-        return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16 or 32, got %d", K);
+    if (!(K == 4 || K == 8 || K == 16 || K == 32 || K == 64))
+        return fail(CS_EUNSUPPORTED, "hidden width must be 4, 8, 16, 32 or 64, got %d", K);
     if (!Vh || !coords || !offset || !b1 || !w2 || !b2 || !res || !gVh || !gb1 || !gw2 || !gb2 || !loss_sum)
         return fail(CS_EINVAL, "cs_pde_fused_step: NULL pointer");
     if (!aligned16(Vh) || !aligned16(gVh)) return fail(CS_EINVAL, "cs_pde_fused_step: Vh / gVh must be 16-byte aligned");
@@ -882,12 +886,12 @@ int cs_pde_fused_step(const cs_problem* pb, const float* Vh, const float* coords
     p.pad = pb->padding_mode; p.align = pb->align_corners; p.kernel = pb->kernel;
     p.multicell = pb->multicell; p.index_mode = pb->index_mode;
     const int v = K / 4;
-    const int lshift = (v == 1) ? 0 : (v == 2) ? 1 : (v == 4) ? 2 : 3;
+    const int lshift = (v == 1) ? 0 : (v == 2) ? 1 : (v == 4) ? 2 : (v == 8) ? 3 : 4;
     p.aggregate = aggregate ? 1 : 0;
     using Fn = cudaError_t (*)(cs::FusedParams&, cudaStream_t);
-    static const Fn table[2][4] = {
-        {cs::launch_fused_d2_l0, cs::launch_fused_d2_l1, cs::launch_fused_d2_l2, cs::launch_fused_d2_l3},
-        {cs::launch_fused_d3_l0, cs::launch_fused_d3_l1, cs::launch_fused_d3_l2, cs::launch_fused_d3_l3}};
+    static const Fn table[2][5] = {
+        {cs::launch_fused_d2_l0, cs::launch_fused_d2_l1, cs::launch_fused_d2_l2, cs::launch_fused_d2_l3, cs::launch_fused_d2_l4},
+        {cs::launch_fused_d3_l0, cs::launch_fused_d3_l1, cs::launch_fused_d3_l2, cs::launch_fused_d3_l3, cs::launch_fused_d3_l4}};
     cudaError_t e = table[pb->dim - 2][lshift](p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "fused step kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

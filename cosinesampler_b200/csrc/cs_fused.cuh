@@ -217,7 +217,7 @@ static __global__ void __launch_bounds__(256) cs_bin_scatter_kernel(const float*
 // ---------------------------------------------------------------------------------------------------------
 // Grid-sized mixes with the head's first layer
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MIX_MAXK = 32;
+constexpr int MIX_MAXK = 64;
 
 // Vh[n, t, k] = sum_c W1[k, c] * V[n, c, t]   (channel-first in, channel-last out: the staging transpose of
 // cs_to_channel_last and the first Linear layer in one pass); Vh[N*T, :] = 0 (the texel out-of-bounds corners read)

@@ -1,7 +1,7 @@
 """One-pass fused PIXEL training step (SURVEY section 8f ranks 1 + 2; opt-in, not part of the
 reference's API): `csrc/cs_fused.cuh` behind torch tensors.
 
-For a head `Linear(C,K)-Tanh-Linear(K,1)` (`test_2d.py:42-47`, K in {4, 8, 16, 32}) the whole step of
+For a head `Linear(C,K)-Tanh-Linear(K,1)` (`test_2d.py:42-47`, K in {4, 8, 16, 32, 64}) the whole step of
 `test_2d.py:36-127` + `loss.backward()` -- replicate the coordinates over the cells, sample, sum over
 the cells, head, nested `autograd.grad` for u_a / u_aa, residual, loss, and the triple-backward
 scatters of `modules_2d.py:98-111` -- is
@@ -31,7 +31,7 @@ from . import _lib, ops
 from .autograd import cell_offsets, padding_mode_enum, _kernel_enum, _require_kernel
 from .jet import residual_coefficients, _add_grad
 
-HIDDEN_WIDTHS = (4, 8, 16, 32)
+HIDDEN_WIDTHS = (4, 8, 16, 32, 64)
 MAX_CHANNELS = 64
 MAX_CELLS = 32          # the records of all cells of a tile of points live in shared memory
 

@@ -469,7 +469,7 @@ _warned_fallback = set()
 
 def fused_mode(cells, head, align_corners=True):
     """Which implementation `fused_pde_step(mode='auto')` takes for this head:
-    'onepass' (`fused.OnePassPdeStep`: Linear(C,K)-Tanh-Linear(K,1), K in {4,8,16,32}; one kernel per chunk),
+    'onepass' (`fused.OnePassPdeStep`: Linear(C,K)-Tanh-Linear(K,1), K in {4,8,16,32,64}; one kernel per chunk),
     'jets' (`FusedPdeStep`: jets -> tensor-core head -> scatter, Linear(C,16)-Tanh-Linear(16,1)), or
     'torch_head' (`jet_autograd_step`: jet kernels + the head's chain rule in torch ops)."""
     from . import fused
@@ -498,7 +498,7 @@ def fused_pde_step(cells, coords, head, residual="helmholtz", k2=math.pi ** 2, p
             if key not in _warned_fallback:
                 _warned_fallback.add(key)
                 import warnings
-                warnings.warn("cosinesampler_b200: head %s is not Linear(C,K)-Tanh-Linear(K,1) with K in {4,8,16,32}; "
+                warnings.warn("cosinesampler_b200: head %s is not Linear(C,K)-Tanh-Linear(K,1) with K in {4,8,16,32,64}; "
                               "fused_pde_step runs the jet kernels with the head in torch ops (slower)" % (key,))
     if mode == "onepass":
         from . import fused

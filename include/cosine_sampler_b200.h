@@ -207,7 +207,7 @@ int cs_bin_points(const cs_problem *pb, const float *coords, const float *offset
 
 /* Vh [N*T + 1, K]: Vh[n*T + t, :] = W1 [K, C] applied to input [n, :, t] (channel-first in, channel-last out:
  * the staging transpose and the first Linear layer, test_2d.py:44, in one pass); the extra texel Vh[N*T, :] is
- * set to zero -- out-of-bounds corners of cs_pde_fused_step read it.  K in {4, 8, 16, 32}, C <= 64. */
+ * set to zero -- out-of-bounds corners of cs_pde_fused_step read it.  K in {4, 8, 16, 32, 64}, C <= 64. */
 int cs_head_premix(int32_t N, int32_t C, int64_t T, int32_t K, const float *input, const float *W1,
                    float *Vh, void *stream);
 /* gInput [N, C, T] (= or +=, nullable) = W1^T gVh;  gW1 [K, C] (+=, nullable) = sum_{n,t} gVh[n,t,:] (x) input[n,:,t].
@@ -217,7 +217,7 @@ int cs_head_postmix(int32_t N, int32_t C, int64_t T, int32_t K, const float *gVh
                     const float *input, const float *W1, float *gInput, int32_t accumulate, float *gW1,
                     void *stream);
 
-/* The pass itself (at most 32 cells).  pb describes the MIXED cells: pb->C = K (hidden width, in {4, 8, 16, 32}),
+/* The pass itself (at most 32 cells).  pb describes the MIXED cells: pb->C = K (hidden width, in {4, 8, 16, 32, 64}),
  * pb->field_layout = CS_LAYOUT_CHANNEL_LAST, P = number of points; coords [P, dim] shared by all cells.
  * Residual f = c_u u + c_u3 u^3 + sum_a (c1[a] u_a + c2[a] u_aa) with u = w2 . tanh(H + b1) + b2 and H the
  * sampled mixed cells summed over the N cells; loss_sum [1] += sum_p f^2 (unscaled); gradients of

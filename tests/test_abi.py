@@ -137,6 +137,7 @@ def test_one_pass_entry_points_validate_arguments_without_a_gpu():
     assert lib.cs_bin_points(ctypes.byref(pb), None, None, None, None, None, 0, None) == -1
     assert b"NULL" in lib.cs_last_error()
     assert lib.cs_head_premix(4, 16, 64, 12, None, None, None, None) == -2
+    assert lib.cs_head_premix(4, 16, 64, 128, None, None, None, None) == -2
     assert b"hidden width" in lib.cs_last_error()
     assert lib.cs_head_premix(4, 65, 64, 16, None, None, None, None) == -2
     assert lib.cs_head_premix(4, 16, 64, 16, None, None, None, None) == -1

@@ -71,7 +71,7 @@ def test_bin_points_is_a_texel_grouping_permutation(cuda, dim):
         assert runs.numel() == torch.unique(runs).numel(), "a texel appears in two separate runs"
 
 
-@pytest.mark.parametrize("K", [4, 8, 16, 32])
+@pytest.mark.parametrize("K", [4, 8, 16, 32, 64])
 def test_premix_postmix_match_einsum(cuda, K):
     from cosinesampler_b200 import fused
     gen = torch.Generator().manual_seed(K)
@@ -106,6 +106,8 @@ CASES = [
     (2, (2, 20, 16, 16), "cosine", "laplace", 4),
     (3, (4, 16, 12, 12, 12), "smooth-step", "laplace", 16),
     (3, (2, 8, 10, 10, 10), "cosine", "helmholtz", 32),
+    (2, (4, 8, 24, 24), "cosine", "helmholtz", 64),
+    (3, (3, 4, 9, 9, 9), "smooth-step", "laplace", 64),
 ]
 
 
