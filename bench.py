@@ -444,6 +444,9 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
                                    "over the fused step's time", "achieved": round(fchain_gbs, 1),
                            "peak": peak, "unit": "GB/s per GPU", "frac": round(fchain_gbs / peak, 4)},
     }
+    # the opt-in arm's two numbers also at the top level of the line (same units as value / e2e)
+    out["fused_value"] = out["fused"]["value"]
+    out["fused_e2e_value"] = out["fused"]["e2e"]["value"]
     if ms_j is not None:
         out["fused"]["round1_jets_path"] = {"value": total / (ms_j * 1e-3), "unit": "points/s", "ms_per_step": ms_j,
                                             "note": "jet.FusedPdeStep (jets -> tensor-core head -> scatter, 3 launches "
