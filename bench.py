@@ -56,10 +56,11 @@ def ncu_traffic_bytes(label):
             with open(os.path.join(ROOT, "profiles", rnd, name)) as f:
                 doc = json.load(f)
             if label in doc["kernels"]:
-                return int(doc["kernels"][label]["traffic_bytes"]), doc.get("points_per_launch"), "profiles/%s/%s" % (rnd, name)
+                return (int(doc["kernels"][label]["traffic_bytes"]), doc.get("points_per_launch"),
+                        "profiles/%s/%s" % (rnd, name), doc["kernels"][label].get("warp_instructions"))
         except Exception:
             pass
-    return None, None, None
+    return None, None, None, None
 
 
 def measured_peak_gbs():
@@ -151,14 +152,26 @@ def stage_table(stage, peak):
             for k, v in sorted(stage.items())}
 
 
-def kernel_roofline(stage, top, peak, peak_src, ms_step_total, points_per_launch=None):
+def kernel_roofline(stage, top, peak, peak_src, ms_step_total, points_per_launch=None, sms=148, sm_clock_hz=None):
     v = stage[top]
     a = v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9
     m = v["moved_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9
-    traffic, cap_points, src = ncu_traffic_bytes(top)
+    traffic, cap_points, src, winstr = ncu_traffic_bytes(top)
     if traffic is not None and cap_points and points_per_launch:
         traffic = int(traffic * points_per_launch / float(cap_points))
-    return {"kernel": top, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+    issue = None
+    if winstr and cap_points and points_per_launch and sm_clock_hz:
+        # instruction-issue roofline of a kernel that is not memory-bound: warp instructions per point from the
+        # committed ncu capture x the points of this launch / its measured time, against one warp instruction per
+        # cycle and SM sub-partition (4 per SM)
+        per_point = winstr / float(cap_points)
+        peak_issue = sms * 4 * sm_clock_hz
+        ach = per_point * points_per_launch / (v["ms_avg"] * 1e-3)
+        issue = {"bound": "instruction issue", "warp_instructions_per_point": round(per_point, 1),
+                 "achieved": round(ach / 1e9, 1), "peak": round(peak_issue / 1e9, 1), "unit": "G warp instructions/s",
+                 "frac": round(ach / peak_issue, 4),
+                 "note": "instructions per point from the ncu capture in traffic_source; peak = SMs x 4 schedulers x SM clock"}
+    return {"kernel": top, "issue_roofline": issue, "bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
             "frac": round(a / peak, 4), "achieved_as_moved": round(m, 1), "frac_as_moved": round(m / peak, 4),
             "traffic": traffic, "traffic_source": src, "peak_source": peak_src,
             "launches": v["launches"], "ms_avg": round(v["ms_avg"], 4), "bytes_per_launch": v["bytes_per_launch"],
@@ -436,10 +449,12 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
         "gpu_launches": int(flaunches), "loss": floss_val,
         "speedup_vs_dropin": ms / ms_f,
         "stages": stage_table(fstage, peak),
-        "roofline": kernel_roofline(fstage, ftop, peak, peak_src, ms_f, points_per_launch=min(fchunk, nloc)) if ftop else None,
+        "roofline": kernel_roofline(fstage, ftop, peak, peak_src, ms_f, points_per_launch=min(fchunk, nloc),
+                                    sms=torch.cuda.get_device_properties(device).multi_processor_count,
+                                    sm_clock_hz=(clock_info or {}).get("sm_mhz", 0) and clock_info["sm_mhz"] * 1e6) if ftop else None,
         "roofline_note": "the one-pass kernel moves 4*dim bytes per point plus the two grid-shaped fields: it is bound by "
                          "instruction issue and the L1 / red paths, not by HBM (profiles/README.md); its HBM fraction "
-                         "is reported for completeness",
+                         "is reported for completeness and roofline.issue_roofline gives the fraction of the issue slots",
         "chain_roofline": {"note": "the reference formulation's minimal bytes per step (BASELINE.md section 3) "
                                    "over the fused step's time", "achieved": round(fchain_gbs, 1),
                            "peak": peak, "unit": "GB/s per GPU", "frac": round(fchain_gbs / peak, 4)},
