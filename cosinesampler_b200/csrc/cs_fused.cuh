@@ -32,6 +32,8 @@
 //     needs the points of a warp to agree in corner AND sub-texel shift plus a segmented shuffle per value.
 #pragma once
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "cs_jet.cuh"
 
@@ -506,6 +508,12 @@ struct FusedParams {
 //               behind the last cell (zero in Vh, a dump in gVh): gathers and reds need no predicate
 //   CQ + a    : (w1, m k', -m^2 k'', w0) of axis a: weight of the high corner, d weight / d coordinate of the
 //               high corner, d2 weight / d coordinate^2 of the high corner (opposite signs for the low corner)
+// Record slot of point i of a tile: one spare float4 per 8 points.  The L lanes of a walker read the same record and
+// the walkers of a warp read points PPQ apart: with slot = i their 16-byte records fall on 2 of the 8 bank groups
+// (4 wavefronts per LDS.128 at K = 16; ncu: 40 % of the kernel's shared-memory wavefronts were bank conflicts), with
+// the spare slots they fall on 8 different ones (1 wavefront), for every hidden width; writes stay conflict-free.
+__device__ __forceinline__ int rec_slot(int i) { return i + (i >> 3); }
+
 template <int DIM, int PTS>
 __device__ __forceinline__ void build_fused_record(float4* rec4, int i, const float (&g)[DIM], bool in_range,
                                                    float off, int pad_index, const FusedParams& p) {
@@ -545,34 +553,269 @@ __device__ __forceinline__ void build_fused_record(float4* rec4, int i, const fl
             }
         }
     }
+    const int sl = rec_slot(i);                  // PTS = padded stride of a field
 #pragma unroll
     for (int h = 0; h < CQ; ++h)
-        rec4[h * PTS + i] = make_float4(__int_as_float(idx[4 * h]), __int_as_float(idx[4 * h + 1]),
-                                        __int_as_float(idx[4 * h + 2]), __int_as_float(idx[4 * h + 3]));
+        rec4[h * PTS + sl] = make_float4(__int_as_float(idx[4 * h]), __int_as_float(idx[4 * h + 1]),
+                                         __int_as_float(idx[4 * h + 2]), __int_as_float(idx[4 * h + 3]));
 #pragma unroll
-    for (int a = 0; a < DIM; ++a) rec4[(CQ + a) * PTS + i] = ax[a];
+    for (int a = 0; a < DIM; ++a) rec4[(CQ + a) * PTS + sl] = ax[a];
 }
 
 __device__ __forceinline__ float tanh_ex2(float x) {
     // one ex2.approx + one rcp.approx: absolute error a few 1e-7 (|tanh| <= 1 is the scale that matters:
     // u = w2 . tanh, s1 = 1 - tanh^2); saturates cleanly to +-1 for large |x|
-    const float e = __expf(-2.f * fabsf(x));
-    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+    // (explicit .ftz forms: __expf / __fdividef without -use_fast_math wrap the MUFU in denormal and range
+    // handling, 37 instructions per tanh instead of 7 -- 16 % of the kernel's instructions, ncu source page)
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.885390081777927f * fabsf(x)));       // exp(-2|x|)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return copysignf((1.f - e) * r, x);
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// One channel of one (x, y) slab: bilinear-type blend with the high-corner weights w1x, w1y (w0 = 1 - w1 for
+// Packed fp32 pairs (fma.rn.f32x2 -> FFMA2, sm_100+): two IEEE fp32 operations per issued instruction.  The FMA
+// pipe delivers the same 128 lanes per clock and SM either way (tools/microbench_ffma2.cu: 120 vs 122), but this
+// kernel is bound by instruction ISSUE (issue slots 66-71 % busy, FMA pipe 43 %), and the 4 hidden units a lane owns
+// are two natural pairs: every per-unit operation below is issued once per pair.  A scalar operand (a weight of the
+// point) is the broadcast form of the instruction (pk(s, s) folds into Rx.F32), a negated operand folds into the
+// operand modifier: neither costs an instruction.  Results are bit-identical to the scalar formulation.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 bc(float s) { return pk(s, s); }
+__device__ __forceinline__ float lo(f2 v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi(f2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ f2 neg2(f2 v) { return pk(-lo(v), -hi(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f4lo(const float4& v) { return pk(v.x, v.y); }
+__device__ __forceinline__ f2 f4hi(const float4& v) { return pk(v.z, v.w); }
+
+// Two channels of one (x, y) slab: bilinear-type blend with the high-corner weights w1x, w1y (w0 = 1 - w1 for
 // all three kernels).  A = value, T = d/dx / (m k'x) = d2/dx2 / (-m^2 k''x), DA = d/dy / (m k'y).
-struct SlabOut { float A, T, DA; };
-__device__ __forceinline__ SlabOut slab_blend(float v00, float v10, float v01, float v11, float w1x, float w1y) {
-    const float d0 = v10 - v00, d1 = v11 - v01;
-    const float a0 = fmaf(d0, w1x, v00), a1 = fmaf(d1, w1x, v01);
+struct SlabOut { f2 A, T, DA; };
+__device__ __forceinline__ SlabOut slab_blend(f2 v00, f2 v10, f2 v01, f2 v11, f2 w1x, f2 w1y) {
+    const f2 d0 = sub2(v10, v00), d1 = sub2(v11, v01);
+    const f2 a0 = fma2(d0, w1x, v00), a1 = fma2(d1, w1x, v01);
     SlabOut o;
-    o.DA = a1 - a0;
-    o.A = fmaf(o.DA, w1y, a0);
-    o.T = fmaf(d1 - d0, w1y, d0);
+    o.DA = sub2(a1, a0);
+    o.A = fma2(o.DA, w1y, a0);
+    o.T = fma2(sub2(d1, d0), w1y, d0);
     return o;
+}
+
+// Per-lane head parameters (hidden units 4j .. 4j+3) and the gradient / loss accumulators of this lane
+struct HeadLane {
+    float b1k[4];
+    f2 w2p[2];
+    float b2;
+    f2 gb1acc[2], gw2acc[2];
+    float gb2acc, lossacc;
+};
+
+__device__ __forceinline__ void init_head_lane(HeadLane& hl, const FusedParams& p, int j) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hl.b1k[k] = __ldg(p.b1 + 4 * j + k);
+    hl.w2p[0] = pk(__ldg(p.w2 + 4 * j), __ldg(p.w2 + 4 * j + 1));
+    hl.w2p[1] = pk(__ldg(p.w2 + 4 * j + 2), __ldg(p.w2 + 4 * j + 3));
+    hl.b2 = __ldg(p.b2);
+    hl.gb1acc[0] = hl.gb1acc[1] = hl.gw2acc[0] = hl.gw2acc[1] = pk(0.f, 0.f);
+    hl.gb2acc = 0.f; hl.lossacc = 0.f;
+}
+
+template <int DIM, int LSHIFT>
+struct FusedGeom {
+    static constexpr int NCORN = 1 << DIM;
+    static constexpr int CQ = NCORN / 4;
+    static constexpr int J = 1 + 2 * DIM;
+    static constexpr int L = 1 << LSHIFT;
+    static constexpr int K = 4 * L;                         // hidden width: 4 units per lane, L lanes per point
+    static constexpr int NW = 32 >> LSHIFT;                 // walkers (point slots) per warp
+    static constexpr int PPQ = (DIM == 2) ? 4 : 2;          // consecutive points per walker and tile
+    static constexpr int PTS = PPQ * NW;                    // points per warp tile
+    static constexpr int PPL = (PTS + 31) / 32;
+    static constexpr int PTSP = PTS + (PTS + 7) / 8;        // padded points per record field (rec_slot)
+    static constexpr int REC1 = (CQ + DIM) * PTSP;          // float4 per record buffer (one cell)
+};
+
+// Phase A for one point (record slot ri): h[jt][hh] = H_jt, hidden units 4j + 2hh, 4j + 2hh + 1, summed over the cells
+template <int DIM, int LSHIFT, int NC>
+__device__ __forceinline__ void fused_gather_point(const FusedParams& p, const float4* recw, int ri, int ncells, int j,
+                                                   f2 (&h)[1 + 2 * DIM][2]) {
+    using G = FusedGeom<DIM, LSHIFT>;
+    constexpr int NCORN = G::NCORN, CQ = G::CQ, J = G::J, K = G::K, PTSP = G::PTSP, REC1 = G::REC1;
+    const f2 zero2 = pk(0.f, 0.f);
+#pragma unroll
+    for (int jt = 0; jt < J; ++jt) { h[jt][0] = zero2; h[jt][1] = zero2; }
+#pragma unroll (NC > 0 ? NC : 2)
+    for (int n = 0; n < ncells; ++n) {
+        const float4* rec = recw + n * REC1;
+        const float* vsrc = p.Vh + (long long)n * p.T * K + 4 * j;
+        float4 v[NCORN];
+#pragma unroll
+        for (int hq = 0; hq < CQ; ++hq) {
+            const float4 ix = rec[hq * PTSP + ri];
+            v[4 * hq + 0] = ldg_f4(vsrc + (long long)__float_as_int(ix.x) * K);
+            v[4 * hq + 1] = ldg_f4(vsrc + (long long)__float_as_int(ix.y) * K);
+            v[4 * hq + 2] = ldg_f4(vsrc + (long long)__float_as_int(ix.z) * K);
+            v[4 * hq + 3] = ldg_f4(vsrc + (long long)__float_as_int(ix.w) * K);
+        }
+        const float4 ax = rec[CQ * PTSP + ri];            // (w1, d, -e, w0)
+        const float4 ay = rec[(CQ + 1) * PTSP + ri];
+        const f2 w1x = bc(ax.x), w1y = bc(ay.x);
+        if (DIM == 2) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const SlabOut o = hh == 0 ? slab_blend(f4lo(v[0]), f4lo(v[1]), f4lo(v[2]), f4lo(v[3]), w1x, w1y)
+                                          : slab_blend(f4hi(v[0]), f4hi(v[1]), f4hi(v[2]), f4hi(v[3]), w1x, w1y);
+                h[0][hh] = add2(h[0][hh], o.A);
+                h[1][hh] = fma2(bc(ax.y), o.T, h[1][hh]);
+                h[2][hh] = fma2(bc(ay.y), o.DA, h[2][hh]);
+                h[3][hh] = fma2(bc(ax.z), o.T, h[3][hh]);
+                h[4][hh] = fma2(bc(ay.z), o.DA, h[4][hh]);
+            }
+        } else {
+            const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTSP + ri];
+            const f2 w1z = bc(az.x);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const SlabOut lo_ = hh == 0 ? slab_blend(f4lo(v[0]), f4lo(v[1]), f4lo(v[2]), f4lo(v[3]), w1x, w1y)
+                                            : slab_blend(f4hi(v[0]), f4hi(v[1]), f4hi(v[2]), f4hi(v[3]), w1x, w1y);
+                const SlabOut hi_ = hh == 0 ? slab_blend(f4lo(v[4 % NCORN]), f4lo(v[5 % NCORN]), f4lo(v[6 % NCORN]), f4lo(v[7 % NCORN]), w1x, w1y)
+                                            : slab_blend(f4hi(v[4 % NCORN]), f4hi(v[5 % NCORN]), f4hi(v[6 % NCORN]), f4hi(v[7 % NCORN]), w1x, w1y);
+                const f2 dA = sub2(hi_.A, lo_.A);
+                const f2 tz = fma2(sub2(hi_.T, lo_.T), w1z, lo_.T);
+                const f2 daz = fma2(sub2(hi_.DA, lo_.DA), w1z, lo_.DA);
+                h[0][hh] = add2(h[0][hh], fma2(dA, w1z, lo_.A));
+                h[1][hh] = fma2(bc(ax.y), tz, h[1][hh]);
+                h[2][hh] = fma2(bc(ay.y), daz, h[2][hh]);
+                h[DIM][hh] = fma2(bc(az.y), dA, h[DIM][hh]);
+                h[1 + DIM][hh] = fma2(bc(ax.z), tz, h[1 + DIM][hh]);
+                h[(2 + DIM) % J][hh] = fma2(bc(ay.z), daz, h[(2 + DIM) % J][hh]);
+                h[2 * DIM][hh] = fma2(bc(az.z), dA, h[2 * DIM][hh]);
+            }
+        }
+    }
+
+}
+
+// Phase B for one point: head + residual + loss, and d loss / d H_jt in place of h
+template <int DIM, int LSHIFT>
+__device__ __forceinline__ void fused_head_point(const FusedParams& p, HeadLane& hl, bool valid, int j,
+                                                 f2 (&h)[1 + 2 * DIM][2]) {
+    constexpr int L = 1 << LSHIFT;
+    // B: head + residual + loss, and d loss / d H_jt in place (test_2d.py:42-127 in closed form):
+    //   t = tanh h, s1 = 1 - t^2, s2 = -2 t s1, s3 = -2 (s1^2 + t s2)
+    //   u = w2.t + b2, u_a = w2.(s1 hd_a), u_aa = w2.(s2 hd_a^2 + s1 hdd_a)
+    f2 th[2], s1[2], ws1[2], ws2[2];
+    const f2 zero2 = pk(0.f, 0.f);
+    f2 ppu = zero2, ppua[DIM], ppuaa[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { ppua[a] = zero2; ppuaa[a] = zero2; }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        th[hh] = pk(tanh_ex2(lo(h[0][hh]) + hl.b1k[2 * hh]), tanh_ex2(hi(h[0][hh]) + hl.b1k[2 * hh + 1]));
+        s1[hh] = fma2(neg2(th[hh]), th[hh], bc(1.f));
+        ws1[hh] = mul2(hl.w2p[hh], s1[hh]);                                 // w2 s1
+        ws2[hh] = mul2(mul2(bc(-2.f), th[hh]), ws1[hh]);                 // w2 s2
+        ppu = fma2(hl.w2p[hh], th[hh], ppu);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            const f2 hd = h[1 + a][hh];
+            ppua[a] = fma2(ws1[hh], hd, ppua[a]);
+            ppuaa[a] = fma2(ws2[hh], mul2(hd, hd), fma2(ws1[hh], h[1 + DIM + a][hh], ppuaa[a]));
+        }
+    }
+    float pu = lo(ppu) + hi(ppu), pua[DIM], puaa[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { pua[a] = lo(ppua[a]) + hi(ppua[a]); puaa[a] = lo(ppuaa[a]) + hi(ppuaa[a]); }
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+        pu += __shfl_xor_sync(0xffffffffu, pu, o);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            pua[a] += __shfl_xor_sync(0xffffffffu, pua[a], o);
+            puaa[a] += __shfl_xor_sync(0xffffffffu, puaa[a], o);
+        }
+    }
+    const float u = pu + hl.b2;
+    float f = p.c_u * u + p.c_u3 * u * u * u;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) f += p.c1[a] * pua[a] + p.c2[a] * puaa[a];
+    const float gg = valid ? 2.f * p.scale * f : 0.f;
+    const float gsc = gg * (p.c_u + 3.f * p.c_u3 * u * u);
+    if (j == 0) {
+        if (valid) hl.lossacc = fmaf(f, f, hl.lossacc);
+        hl.gb2acc += gsc;
+    }
+    float g1c[DIM], g2c[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { g1c[a] = gg * p.c1[a]; g2c[a] = gg * p.c2[a]; }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        // with G1 = sum_a g1c_a hd_a + g2c_a hdd_a and G2 = sum_a g2c_a hd_a^2:
+        //   d loss / d w2_k = gsc t + s1 G1 + s2 G2        d loss / d h_k = w2 (gsc s1 + s2 G1 + s3 G2)
+        const f2 ws3 = mul2(bc(-2.f), fma2(ws1[hh], s1[hh], mul2(th[hh], ws2[hh])));      // w2 s3
+        f2 G1 = zero2, G2 = zero2;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            const f2 hd = h[1 + a][hh];
+            const f2 gh2 = mul2(bc(g2c[a]), hd);
+            G1 = fma2(bc(g1c[a]), hd, fma2(bc(g2c[a]), h[1 + DIM + a][hh], G1));
+            G2 = fma2(gh2, hd, G2);
+            h[1 + a][hh] = fma2(ws1[hh], bc(g1c[a]), mul2(mul2(bc(2.f), ws2[hh]), gh2));
+            h[1 + DIM + a][hh] = mul2(ws1[hh], bc(g2c[a]));
+        }
+        const f2 gh = fma2(ws3, G2, fma2(ws2[hh], G1, mul2(ws1[hh], bc(gsc))));
+        const f2 gw2 = fma2(mul2(mul2(bc(-2.f), th[hh]), s1[hh]), G2, fma2(s1[hh], G1, mul2(bc(gsc), th[hh])));
+        h[0][hh] = gh;
+        hl.gb1acc[hh] = add2(hl.gb1acc[hh], gh);
+        hl.gw2acc[hh] = add2(hl.gw2acc[hh], gw2);
+    }
+}
+
+// Head-parameter gradients and loss: walkers of a warp (shuffles) -> warps (shared memory) -> one atomic per block
+// and element.  smem4 is reused: every warp must be done with its records (the barrier inside).
+template <int LSHIFT>
+__device__ __forceinline__ void fused_reduce_head(const FusedParams& p, HeadLane& hl, float4* smem4, int lane, int warp,
+                                                  int wpb) {
+    constexpr int L = 1 << LSHIFT;
+    constexpr int K = 4 * L;
+    const int q = lane >> LSHIFT;
+    const int j = lane & (L - 1);
+    // ---- head-parameter gradients and loss: walkers of a warp (shuffles) -> warps (shared memory) -> one
+    // atomic per block and element
+    float gb1s[4] = {lo(hl.gb1acc[0]), hi(hl.gb1acc[0]), lo(hl.gb1acc[1]), hi(hl.gb1acc[1])};
+    float gw2s[4] = {lo(hl.gw2acc[0]), hi(hl.gw2acc[0]), lo(hl.gw2acc[1]), hi(hl.gw2acc[1])};
+#pragma unroll
+    for (int o = L; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gb1s[k] += __shfl_xor_sync(0xffffffffu, gb1s[k], o);
+            gw2s[k] += __shfl_xor_sync(0xffffffffu, gw2s[k], o);
+        }
+        hl.gb2acc += __shfl_xor_sync(0xffffffffu, hl.gb2acc, o);
+        hl.lossacc += __shfl_xor_sync(0xffffffffu, hl.lossacc, o);
+    }
+    __syncthreads();                                 // every warp is done with its records
+    float* red = reinterpret_cast<float*>(smem4);    // [wpb][2K + 2]
+    constexpr int RW = 2 * K + 2;
+    if (q == 0) {
+        float* rw = red + warp * RW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rw[4 * j + k] = gb1s[k]; rw[K + 4 * j + k] = gw2s[k]; }
+        if (j == 0) { rw[2 * K] = hl.gb2acc; rw[2 * K + 1] = hl.lossacc; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < RW; e += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < wpb; ++w) s += red[w * RW + e];
+        float* dst = (e < K) ? p.gb1 + e : (e < 2 * K) ? p.gw2 + (e - K) : (e == 2 * K) ? p.gb2 : p.loss_sum;
+        atomicAdd(dst, s);
+    }
 }
 
 #ifndef CS_FUSED_BLOCKS
@@ -610,7 +853,8 @@ cs_pde_fused_kernel(const FusedParams p) {
     constexpr int PPQ = (DIM == 2) ? 4 : 2;          // consecutive points per walker and tile
     constexpr int PTS = PPQ * NW;                    // points per warp tile
     constexpr int PPL = (PTS + 31) / 32;
-    constexpr int REC1 = (CQ + DIM) * PTS;           // float4 per record buffer (one cell)
+    constexpr int PTSP = PTS + (PTS + 7) / 8;        // padded points per record field (rec_slot)
+    constexpr int REC1 = (CQ + DIM) * PTSP;          // float4 per record buffer (one cell)
 
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31;
@@ -621,12 +865,9 @@ cs_pde_fused_kernel(const FusedParams p) {
     const int ncells = NC > 0 ? NC : p.N;
     float4* recw = smem4 + (size_t)warp * ncells * REC1;
 
-    float b1k[4], w2k[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { b1k[k] = __ldg(p.b1 + 4 * j + k); w2k[k] = __ldg(p.w2 + 4 * j + k); }
-    const float b2 = __ldg(p.b2);
-    float gb1acc[4] = {0.f, 0.f, 0.f, 0.f}, gw2acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float gb2acc = 0.f, lossacc = 0.f;
+    HeadLane hl;
+    init_head_lane(hl, p, j);
+    const f2 zero2 = pk(0.f, 0.f);
 
     const long long gw = (long long)blockIdx.x * wpb + warp;
     const long long tile_begin = gw * p.tiles_per_warp;
@@ -679,153 +920,36 @@ cs_pde_fused_kernel(const FusedParams p) {
                 for (int u = 0; u < PPL; ++u) {
                     const int i = (u * 32 + lane) % PTS;
                     if (u * 32 + lane < PTS * CPL)
-                        build_fused_record<DIM, PTS>(recw + n * REC1, i, gcur[u], icur[u], off, pad_index, p);
+                        build_fused_record<DIM, PTSP>(recw + n * REC1, i, gcur[u], icur[u], off, pad_index, p);
                 }
             }
         }
         __syncwarp();                                   // records are visible
 
-        // acc[jt][t][k] = d loss / d H_jt of point t of this walker, hidden unit 4j + k
-        float acc[J][PPQ][4];
+        // acc[jt][t][h] = d loss / d H_jt of point t of this walker, hidden units 4j + 2h, 4j + 2h + 1
+        f2 acc[J][PPQ][2];
 #pragma unroll
         for (int jt = 0; jt < J; ++jt)
 #pragma unroll
-            for (int t = 0; t < PPQ; ++t)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[jt][t][k] = 0.f;
+            for (int t = 0; t < PPQ; ++t) { acc[jt][t][0] = zero2; acc[jt][t][1] = zero2; }
 
         // ---- A + B, one point at a time
 #pragma unroll 1
         for (int t = 0; t < PPQ; ++t) {
-            const int ri = PPQ * q + t;
-            // A: gather.  h[jt][k] = H_jt of this point, hidden unit 4j + k, summed over the cells
-            float h[J][4];
-#pragma unroll
-            for (int jt = 0; jt < J; ++jt)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h[jt][k] = 0.f;
-#pragma unroll (NC > 0 ? NC : 2)
-            for (int n = 0; n < ncells; ++n) {
-                const float4* rec = recw + n * REC1;
-                const float* vsrc = p.Vh + (long long)n * p.T * K + 4 * j;
-                float4 v[NCORN];
-#pragma unroll
-                for (int hq = 0; hq < CQ; ++hq) {
-                    const float4 ix = rec[hq * PTS + ri];
-                    v[4 * hq + 0] = ldg_f4(vsrc + (long long)__float_as_int(ix.x) * K);
-                    v[4 * hq + 1] = ldg_f4(vsrc + (long long)__float_as_int(ix.y) * K);
-                    v[4 * hq + 2] = ldg_f4(vsrc + (long long)__float_as_int(ix.z) * K);
-                    v[4 * hq + 3] = ldg_f4(vsrc + (long long)__float_as_int(ix.w) * K);
-                }
-                const float4 ax = rec[CQ * PTS + ri];            // (w1, d, -e, w0)
-                const float4 ay = rec[(CQ + 1) * PTS + ri];
-                if (DIM == 2) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const SlabOut o = slab_blend(f4get(v[0], k), f4get(v[1], k), f4get(v[2], k), f4get(v[3], k), ax.x, ay.x);
-                        h[0][k] += o.A;
-                        h[1][k] = fmaf(ax.y, o.T, h[1][k]);
-                        h[2][k] = fmaf(ay.y, o.DA, h[2][k]);
-                        h[3][k] = fmaf(ax.z, o.T, h[3][k]);
-                        h[4][k] = fmaf(ay.z, o.DA, h[4][k]);
-                    }
-                } else {
-                    const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTS + ri];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const SlabOut lo = slab_blend(f4get(v[0], k), f4get(v[1], k), f4get(v[2], k), f4get(v[3], k), ax.x, ay.x);
-                        const SlabOut hi = slab_blend(f4get(v[4 % NCORN], k), f4get(v[5 % NCORN], k), f4get(v[6 % NCORN], k),
-                                                      f4get(v[7 % NCORN], k), ax.x, ay.x);
-                        const float dA = hi.A - lo.A;
-                        const float tz = fmaf(hi.T - lo.T, az.x, lo.T);
-                        const float daz = fmaf(hi.DA - lo.DA, az.x, lo.DA);
-                        h[0][k] += fmaf(dA, az.x, lo.A);
-                        h[1][k] = fmaf(ax.y, tz, h[1][k]);
-                        h[2][k] = fmaf(ay.y, daz, h[2][k]);
-                        h[DIM][k] = fmaf(az.y, dA, h[DIM][k]);
-                        h[1 + DIM][k] = fmaf(ax.z, tz, h[1 + DIM][k]);
-                        h[(2 + DIM) % J][k] = fmaf(ay.z, daz, h[(2 + DIM) % J][k]);
-                        h[2 * DIM][k] = fmaf(az.z, dA, h[2 * DIM][k]);
-                    }
-                }
-            }
-
-            // B: head + residual + loss, and d loss / d H_jt in place (test_2d.py:42-127 in closed form):
-            //   t = tanh h, s1 = 1 - t^2, s2 = -2 t s1, s3 = -2 (s1^2 + t s2)
-            //   u = w2.t + b2, u_a = w2.(s1 hd_a), u_aa = w2.(s2 hd_a^2 + s1 hdd_a)
-            float th[4], ws1[4], ws2[4];
-            float pu = 0.f, pua[DIM], puaa[DIM];
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) { pua[a] = 0.f; puaa[a] = 0.f; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                th[k] = tanh_ex2(h[0][k] + b1k[k]);
-                const float s1 = fmaf(-th[k], th[k], 1.f);
-                ws1[k] = w2k[k] * s1;                            // w2 s1
-                ws2[k] = -2.f * th[k] * ws1[k];                  // w2 s2
-                pu = fmaf(w2k[k], th[k], pu);
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const float hd = h[1 + a][k];
-                    pua[a] = fmaf(ws1[k], hd, pua[a]);
-                    puaa[a] = fmaf(ws2[k], hd * hd, fmaf(ws1[k], h[1 + DIM + a][k], puaa[a]));
-                }
-            }
-#pragma unroll
-            for (int o = 1; o < L; o <<= 1) {
-                pu += __shfl_xor_sync(0xffffffffu, pu, o);
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    pua[a] += __shfl_xor_sync(0xffffffffu, pua[a], o);
-                    puaa[a] += __shfl_xor_sync(0xffffffffu, puaa[a], o);
-                }
-            }
-            const float u = pu + b2;
-            float f = p.c_u * u + p.c_u3 * u * u * u;
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) f += p.c1[a] * pua[a] + p.c2[a] * puaa[a];
-            const bool valid = qp0 + t < p.P;
-            const float gg = valid ? 2.f * p.scale * f : 0.f;
-            const float gsc = gg * (p.c_u + 3.f * p.c_u3 * u * u);
-            if (j == 0) {
-                if (valid) lossacc = fmaf(f, f, lossacc);
-                gb2acc += gsc;
-            }
-            float g1c[DIM], g2c[DIM];
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) { g1c[a] = gg * p.c1[a]; g2c[a] = gg * p.c2[a]; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // with G1 = sum_a g1c_a hd_a + g2c_a hdd_a and G2 = sum_a g2c_a hd_a^2:
-                //   d loss / d w2_k = gsc t + s1 G1 + s2 G2        d loss / d h_k = w2 (gsc s1 + s2 G1 + s3 G2)
-                const float s1 = fmaf(-th[k], th[k], 1.f);
-                const float ws3 = -2.f * fmaf(ws1[k], s1, th[k] * ws2[k]);      // w2 s3
-                float G1 = 0.f, G2 = 0.f;
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const float hd = h[1 + a][k];
-                    const float gh2 = g2c[a] * hd;
-                    G1 = fmaf(g1c[a], hd, fmaf(g2c[a], h[1 + DIM + a][k], G1));
-                    G2 = fmaf(gh2, hd, G2);
-                    h[1 + a][k] = fmaf(ws1[k], g1c[a], 2.f * ws2[k] * gh2);
-                    h[1 + DIM + a][k] = ws1[k] * g2c[a];
-                }
-                const float gh = fmaf(ws3, G2, fmaf(ws2[k], G1, ws1[k] * gsc));
-                const float gw2 = fmaf(-2.f * th[k] * s1, G2, fmaf(s1, G1, gsc * th[k]));
-                h[0][k] = gh;
-                gb1acc[k] += gh;
-                gw2acc[k] += gw2;
-            }
+            const int ri = rec_slot(PPQ * q + t);
+            f2 h[J][2];
+            fused_gather_point<DIM, LSHIFT, NC>(p, recw, ri, ncells, j, h);
+            fused_head_point<DIM, LSHIFT>(p, hl, qp0 + t < p.P, j, h);
             // the finished point enters the register tile at the top; after PPQ rounds point t sits in slot t
             // (registers cannot be indexed by t; a warp-uniform switch over the slot measured 3 % slower than
             // these moves)
 #pragma unroll
             for (int jt = 0; jt < J; ++jt)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                    for (int s = 0; s + 1 < PPQ; ++s) acc[jt][s][k] = acc[jt][s + 1][k];
-                    acc[jt][PPQ - 1][k] = h[jt][k];
+                    for (int sl = 0; sl + 1 < PPQ; ++sl) acc[jt][sl][hh] = acc[jt][sl + 1][hh];
+                    acc[jt][PPQ - 1][hh] = h[jt][hh];
                 }
         }
 
@@ -835,55 +959,57 @@ cs_pde_fused_kernel(const FusedParams p) {
         for (int n = 0; n < ncells; ++n) {
             const float4* rec = recw + n * REC1;
             float* gcell = p.gVh + (long long)n * p.T * K + 4 * j;
-            float cur[NCORN][4];
+            f2 cur[NCORN][2];
             int cix[NCORN];
 #pragma unroll
             for (int t = 0; t < PPQ; ++t) {
-                const int ri = PPQ * q + t;
+                const int ri = rec_slot(PPQ * q + t);
                 int ix[NCORN];
 #pragma unroll
                 for (int hq = 0; hq < CQ; ++hq) {
-                    const float4 f = rec[hq * PTS + ri];
+                    const float4 f = rec[hq * PTSP + ri];
                     ix[4 * hq] = __float_as_int(f.x); ix[4 * hq + 1] = __float_as_int(f.y);
                     ix[4 * hq + 2] = __float_as_int(f.z); ix[4 * hq + 3] = __float_as_int(f.w);
                 }
-                const float4 ax = rec[CQ * PTS + ri];            // (w1, d, -e, w0)
-                const float4 ay = rec[(CQ + 1) * PTS + ri];
-                float cv[NCORN][4];
+                const float4 ax = rec[CQ * PTSP + ri];            // (w1, d, -e, w0)
+                const float4 ay = rec[(CQ + 1) * PTSP + ri];
+                f2 cv[NCORN][2];
                 if (DIM == 2) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float alpha = fmaf(acc[3][t][k], ax.z, acc[1][t][k] * ax.y);
-                        const float beta = fmaf(acc[4][t][k], ay.z, acc[2][t][k] * ay.y);
-                        const float u0 = fmaf(acc[0][t][k], ax.w, -alpha);
-                        const float u1 = fmaf(acc[0][t][k], ax.x, alpha);
-                        const float bx0 = ax.w * beta, bx1 = ax.x * beta;
-                        cv[0][k] = fmaf(ay.w, u0, -bx0);
-                        cv[1][k] = fmaf(ay.w, u1, -bx1);
-                        cv[2][k] = fmaf(ay.x, u0, bx0);
-                        cv[3][k] = fmaf(ay.x, u1, bx1);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const f2 alpha = fma2(acc[3][t][hh], bc(ax.z), mul2(acc[1][t][hh], bc(ax.y)));
+                        const f2 beta = fma2(acc[4][t][hh], bc(ay.z), mul2(acc[2][t][hh], bc(ay.y)));
+                        const f2 u0 = fma2(acc[0][t][hh], bc(ax.w), neg2(alpha));
+                        const f2 u1 = fma2(acc[0][t][hh], bc(ax.x), alpha);
+                        const f2 bx0 = mul2(bc(ax.w), beta), bx1 = mul2(bc(ax.x), beta);
+                        cv[0][hh] = fma2(bc(ay.w), u0, neg2(bx0));
+                        cv[1][hh] = fma2(bc(ay.w), u1, neg2(bx1));
+                        cv[2][hh] = fma2(bc(ay.x), u0, bx0);
+                        cv[3][hh] = fma2(bc(ay.x), u1, bx1);
                     }
                 } else {
-                    const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTS + ri];
+                    const float4 az = rec[(CQ + (DIM == 3 ? 2 : 1)) * PTSP + ri];
                     const float p00 = ax.w * ay.w, p10 = ax.x * ay.w, p01 = ax.w * ay.x, p11 = ax.x * ay.x;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float alpha = fmaf(acc[1 + DIM][t][k], ax.z, acc[1][t][k] * ax.y);
-                        const float beta = fmaf(acc[(2 + DIM) % J][t][k], ay.z, acc[2][t][k] * ay.y);
-                        const float gamma = fmaf(acc[2 * DIM][t][k], az.z, acc[DIM][t][k] * az.y);
-                        const float u0 = fmaf(acc[0][t][k], ax.w, -alpha);
-                        const float u1 = fmaf(acc[0][t][k], ax.x, alpha);
-                        const float bx0 = ax.w * beta, bx1 = ax.x * beta;
-                        const float c00 = fmaf(ay.w, u0, -bx0), c10 = fmaf(ay.w, u1, -bx1);
-                        const float c01 = fmaf(ay.x, u0, bx0), c11 = fmaf(ay.x, u1, bx1);
-                        cv[0][k] = fmaf(az.w, c00, -p00 * gamma);
-                        cv[1][k] = fmaf(az.w, c10, -p10 * gamma);
-                        cv[2][k] = fmaf(az.w, c01, -p01 * gamma);
-                        cv[3][k] = fmaf(az.w, c11, -p11 * gamma);
-                        cv[4 % NCORN][k] = fmaf(az.x, c00, p00 * gamma);
-                        cv[5 % NCORN][k] = fmaf(az.x, c10, p10 * gamma);
-                        cv[6 % NCORN][k] = fmaf(az.x, c01, p01 * gamma);
-                        cv[7 % NCORN][k] = fmaf(az.x, c11, p11 * gamma);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const f2 alpha = fma2(acc[1 + DIM][t][hh], bc(ax.z), mul2(acc[1][t][hh], bc(ax.y)));
+                        const f2 beta = fma2(acc[(2 + DIM) % J][t][hh], bc(ay.z), mul2(acc[2][t][hh], bc(ay.y)));
+                        const f2 gamma = fma2(acc[2 * DIM][t][hh], bc(az.z), mul2(acc[DIM][t][hh], bc(az.y)));
+                        const f2 u0 = fma2(acc[0][t][hh], bc(ax.w), neg2(alpha));
+                        const f2 u1 = fma2(acc[0][t][hh], bc(ax.x), alpha);
+                        const f2 bx0 = mul2(bc(ax.w), beta), bx1 = mul2(bc(ax.x), beta);
+                        const f2 c00 = fma2(bc(ay.w), u0, neg2(bx0)), c10 = fma2(bc(ay.w), u1, neg2(bx1));
+                        const f2 c01 = fma2(bc(ay.x), u0, bx0), c11 = fma2(bc(ay.x), u1, bx1);
+                        const f2 g00 = mul2(bc(p00), gamma), g10 = mul2(bc(p10), gamma);
+                        const f2 g01 = mul2(bc(p01), gamma), g11 = mul2(bc(p11), gamma);
+                        cv[0][hh] = fma2(bc(az.w), c00, neg2(g00));
+                        cv[1][hh] = fma2(bc(az.w), c10, neg2(g10));
+                        cv[2][hh] = fma2(bc(az.w), c01, neg2(g01));
+                        cv[3][hh] = fma2(bc(az.w), c11, neg2(g11));
+                        cv[4 % NCORN][hh] = fma2(bc(az.x), c00, g00);
+                        cv[5 % NCORN][hh] = fma2(bc(az.x), c10, g10);
+                        cv[6 % NCORN][hh] = fma2(bc(az.x), c01, g01);
+                        cv[7 % NCORN][hh] = fma2(bc(az.x), c11, g11);
                     }
                 }
                 if (t > 0) {
@@ -892,25 +1018,26 @@ cs_pde_fused_kernel(const FusedParams p) {
                     for (int c = 0; c < NCORN; ++c) same = same && (ix[c] == cix[c]);
                     if (same) {
 #pragma unroll
-                        for (int c = 0; c < NCORN; ++c)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) cv[c][k] += cur[c][k];
+                        for (int c = 0; c < NCORN; ++c) {
+                            cv[c][0] = add2(cv[c][0], cur[c][0]);
+                            cv[c][1] = add2(cv[c][1], cur[c][1]);
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < NCORN; ++c)
-                            red_add_v4(gcell + (long long)cix[c] * K, cur[c][0], cur[c][1], cur[c][2], cur[c][3]);
+                            red_add_v4(gcell + (long long)cix[c] * K, lo(cur[c][0]), hi(cur[c][0]), lo(cur[c][1]), hi(cur[c][1]));
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < NCORN; ++c) {
                     cix[c] = ix[c];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cur[c][k] = cv[c][k];
+                    cur[c][0] = cv[c][0];
+                    cur[c][1] = cv[c][1];
                 }
             }
 #pragma unroll
             for (int c = 0; c < NCORN; ++c)
-                red_add_v4(gcell + (long long)cix[c] * K, cur[c][0], cur[c][1], cur[c][2], cur[c][3]);
+                red_add_v4(gcell + (long long)cix[c] * K, lo(cur[c][0]), hi(cur[c][0]), lo(cur[c][1]), hi(cur[c][1]));
         }
 
         if (have_next) {
@@ -923,34 +1050,7 @@ cs_pde_fused_kernel(const FusedParams p) {
         }
     }
 
-    // ---- head-parameter gradients and loss: walkers of a warp (shuffles) -> warps (shared memory) -> one
-    // atomic per block and element
-#pragma unroll
-    for (int o = L; o < 32; o <<= 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            gb1acc[k] += __shfl_xor_sync(0xffffffffu, gb1acc[k], o);
-            gw2acc[k] += __shfl_xor_sync(0xffffffffu, gw2acc[k], o);
-        }
-        gb2acc += __shfl_xor_sync(0xffffffffu, gb2acc, o);
-        lossacc += __shfl_xor_sync(0xffffffffu, lossacc, o);
-    }
-    __syncthreads();                                 // every warp is done with its records
-    float* red = reinterpret_cast<float*>(smem4);    // [wpb][2K + 2]
-    constexpr int RW = 2 * K + 2;
-    if (q == 0) {
-        float* rw = red + warp * RW;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { rw[4 * j + k] = gb1acc[k]; rw[K + 4 * j + k] = gw2acc[k]; }
-        if (j == 0) { rw[2 * K] = gb2acc; rw[2 * K + 1] = lossacc; }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < RW; e += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < wpb; ++w) s += red[w * RW + e];
-        float* dst = (e < K) ? p.gb1 + e : (e < 2 * K) ? p.gw2 + (e - K) : (e == 2 * K) ? p.gb2 : p.loss_sum;
-        atomicAdd(dst, s);
-    }
+    fused_reduce_head<LSHIFT>(p, hl, smem4, lane, warp, wpb);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -962,9 +1062,9 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     constexpr int K = 4 << LSHIFT;
     constexpr int PPQ = (DIM == 2) ? 4 : 2;
     constexpr int PTS = PPQ * NW;
-    constexpr int REC1 = ((1 << DIM) / 4 + DIM) * PTS;
-    auto kern = (p.N == 4) ? cs_pde_fused_kernel<DIM, LSHIFT, 4> : cs_pde_fused_kernel<DIM, LSHIFT, 0>;
+    constexpr int REC1 = ((1 << DIM) / 4 + DIM) * (PTS + (PTS + 7) / 8);
     if (p.N > FUSED_MAX_CELLS) return cudaErrorInvalidConfiguration;
+    auto kern = (p.N == 4) ? cs_pde_fused_kernel<DIM, LSHIFT, 4> : cs_pde_fused_kernel<DIM, LSHIFT, 0>;
     const size_t per_warp = (size_t)p.N * REC1 * sizeof(float4);
     int wpb = FUSED_THREADS / 32;
     while (wpb > 1 && wpb * per_warp > 72 * 1024) wpb >>= 1;      // three blocks per SM where the records allow

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run the one-pass fused step twice on 2^22 points of config 3 (2D) or config 4 (3D) so that
+"""Run the one-pass fused step twice on 2^22 points (or argv[2] points) of config 3 (2D) or config 4 (3D) so that
 `ncu -k regex:cs_pde_fused` captures one warm-up launch and one launch to keep (tools/summarize_ncu.py
 onepass_cfg3 / onepass_cfg4)."""
 import os
@@ -18,7 +18,8 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 cells = torch.nn.Parameter(torch.rand(shape, generator=g).to(dev))
 head = chain.make_head(shape[1], seed=0, device=dev)
-coords = (torch.rand(2 ** 22, dim, generator=g) * 2 - 1).to(dev)
+P = int(sys.argv[2]) if len(sys.argv) > 2 else 2 ** 22
+coords = (torch.rand(P, dim, generator=g) * 2 - 1).to(dev)
 for _ in range(2):
     cells.grad = None
     loss = fused.one_pass_pde_step(cells, coords, head, residual, kernel=kernel)
