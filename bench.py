@@ -45,10 +45,11 @@ CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tenso
 
 def ncu_traffic_bytes(label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed
-    `ncu --set full` captures of the same shapes (profiles/r2/*_summary.json, else profiles/r1/...; the
-    captures drive the same call pattern as this bench: an expanded gOut for the stage kernels, 2^22
-    binned points per launch for the one-pass kernel).  -> (bytes, points per launch of the capture)"""
-    for rnd, name in (("r2", "ncu_stages_cfg3_summary.json"), ("r2", "ncu_stages_cfg4_summary.json"),
+    `ncu --set full` captures of the same shapes (profiles/r3/*_summary.json, else profiles/r2/, r1/; the
+    captures drive the same call pattern as this bench: an expanded gOut for the stage kernels, 2^25 (2D) /
+    2^22 (3D) binned points per launch for the one-pass kernel).  -> (bytes, points per launch of the capture)"""
+    for rnd, name in (("r3", "ncu_onepass_cfg3_summary.json"), ("r3", "ncu_onepass_cfg4_summary.json"),
+                      ("r2", "ncu_stages_cfg3_summary.json"), ("r2", "ncu_stages_cfg4_summary.json"),
                       ("r2", "ncu_onepass_cfg3_summary.json"), ("r2", "ncu_onepass_cfg4_summary.json"),
                       ("r1", "ncu_stages_cfg3_summary.json"), ("r1", "ncu_stages_cfg4_summary.json"),
                       ("r1", "ncu_fused_cfg3_summary.json"), ("r1", "ncu_fused_cfg4_summary.json")):
@@ -269,6 +270,24 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
             ev.record(copy_stream)
         return t, ev
 
+    def h2d_probe():
+        """Bandwidth of the copy the end-to-end arms depend on: the rank's pinned coordinates to the device,
+        alone on the copy stream (best of 3).  A box whose host memory system is slow shows up here."""
+        best = None
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(copy_stream):
+                e0.record(copy_stream)
+                t = coords_pinned.to(device, non_blocking=True)
+                e1.record(copy_stream)
+            torch.cuda.synchronize()
+            del t
+            ms_ = e0.elapsed_time(e1)
+            best = ms_ if best is None else min(best, ms_)
+        return coords_pinned.numel() * 4 / (best * 1e-3) / 1e9 if best and best > 0 else None
+
     def step_e2e():
         """Same step from HOST buffers: every chunk of coordinates is copied from pinned host
         memory inside the timed region (on a copy stream, one chunk ahead of the compute stream) and
@@ -354,6 +373,7 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
     if world > 1:
         dist.all_reduce(loss_t)                      # each rank holds its share of the mean
     loss_val = float(loss_t.item())
+    h2d_gbs = h2d_probe()
     for _ in range(max(1, min(warmup, 2))):
         step_e2e()
     ms_e2e = timed(step_e2e, steps)
@@ -410,7 +430,7 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
                          % (4 * N * C * min(chunk, total) // 2 ** 20)},
         "e2e": {"value": total * steps / (ms_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / steps},
+                "ms_per_step": ms_e2e / steps, "h2d_GBps_alone": round(h2d_gbs, 1) if h2d_gbs else None},
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": kernel_roofline(stage, top, peak, peak_src, ms) if top else None,
@@ -445,7 +465,8 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
         "ms_per_2^20_points": round(ms_f / steps * 2 ** 20 * world / total, 4),
         "e2e": {"value": total * steps / (ms_f_e2e * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": coords_pinned.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_f_e2e / steps},
+                "ms_per_step": ms_f_e2e / steps, "h2d_GBps_alone": round(h2d_gbs, 1) if h2d_gbs else None,
+                "h2d_ms_alone": round(coords_pinned.numel() * 4 / (h2d_gbs * 1e9) * 1e3, 3) if h2d_gbs else None},
         "gpu_launches": int(flaunches), "loss": floss_val,
         "speedup_vs_dropin": ms / ms_f,
         "stages": stage_table(fstage, peak),

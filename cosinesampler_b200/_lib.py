@@ -15,6 +15,7 @@ EXPORTS = (
     "cs_forward", "cs_backward", "cs_backward_backward", "cs_backward_backward_backward",
     "cs_to_channel_last", "cs_from_channel_last",
     "cs_forward_f64", "cs_backward_f64", "cs_backward_backward_f64", "cs_backward_backward_backward_f64",
+    "cs_forward_f16", "cs_backward_f16", "cs_backward_backward_f16", "cs_backward_backward_backward_f16",
     "cs_jet_forward", "cs_jet_backward", "cs_pde_head_step", "cs_peer_allreduce_from_channel_last",
     "cs_peer_allreduce",
     "cs_bin_workspace_bytes", "cs_bin_points", "cs_head_premix", "cs_head_postmix", "cs_pde_fused_step",
@@ -90,6 +91,14 @@ def load():
     lib.cs_backward_backward_f64.argtypes = [pp, vp, vp, vp, vp, Stream3, vp, vp, vp, vp, vp]
     lib.cs_backward_backward_backward_f64.restype = ctypes.c_int
     lib.cs_backward_backward_backward_f64.argtypes = [pp, vp, vp, Stream3, vp, vp, Stream3, vp, vp, vp, vp]
+    lib.cs_forward_f16.restype = ctypes.c_int
+    lib.cs_forward_f16.argtypes = [pp, vp, vp, vp, vp, vp]
+    lib.cs_backward_f16.restype = ctypes.c_int
+    lib.cs_backward_f16.argtypes = [pp, Stream3, vp, vp, vp, vp, vp, vp, vp]
+    lib.cs_backward_backward_f16.restype = ctypes.c_int
+    lib.cs_backward_backward_f16.argtypes = [pp, vp, vp, vp, vp, Stream3, vp, vp, vp, vp, vp, vp]
+    lib.cs_backward_backward_backward_f16.restype = ctypes.c_int
+    lib.cs_backward_backward_backward_f16.argtypes = [pp, vp, vp, Stream3, vp, vp, Stream3, vp, vp, vp, vp, vp]
     lib.cs_jet_forward.restype = ctypes.c_int
     lib.cs_jet_forward.argtypes = [pp, i32, vp, vp, vp, vp, vp]
     lib.cs_jet_backward.restype = ctypes.c_int

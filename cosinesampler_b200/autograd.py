@@ -159,7 +159,7 @@ def _engine_wants(ctx, idx):
 
 
 def _staged_of(offset, input):
-    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+    if isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16):
         return None                      # the double-precision path reads the reference layout directly
     ops._check(input, "input")
     st = getattr(offset, "_cs_staged", None)
@@ -288,7 +288,7 @@ def make_functions(dim):
         @staticmethod
         def forward(ctx, input, grid, padding_mode="zeros", align_corners=True, kernel="cosine",
                     multicell=True):
-            if not (isinstance(input, torch.Tensor) and input.dtype == torch.float64):
+            if not (isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16)):
                 ops._check(input, "input")
                 ops._grid_view(grid)
             offset = cell_offsets(input.shape[0], multicell, input.device)

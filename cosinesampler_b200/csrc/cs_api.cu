@@ -547,7 +547,8 @@ cudaError_t postmix_launch(const float* gVh, const float* V, const float* W1, fl
 // ---------------------------------------------------------------------------
 // Double-precision path (cs_scalar.cuh)
 // ---------------------------------------------------------------------------
-int scalar_setup(const cs_problem* pb, cs::ScalarParams& p, const double* grid, const float* offset) {
+template <typename S>
+int scalar_setup(const cs_problem* pb, cs::ScalarParamsT<S>& p, const S* grid, const float* offset) {
     if (!pb) return fail(CS_EINVAL, "cs_problem is NULL");
     if (pb->dim != 2 && pb->dim != 3) return fail(CS_EINVAL, "dim must be 2 or 3, got %d", pb->dim);
     if (pb->N < 0 || pb->C < 0 || pb->P < 0) return fail(CS_EINVAL, "negative size");
@@ -556,7 +557,7 @@ int scalar_setup(const cs_problem* pb, cs::ScalarParams& p, const double* grid, 
     if (pb->padding_mode < 0 || pb->padding_mode > 2) return fail(CS_EINVAL, "bad padding_mode %d", pb->padding_mode);
     if (pb->kernel < 0 || pb->kernel > 2) return fail(CS_EINVAL, "bad kernel %d", pb->kernel);
     if (pb->field_layout != CS_LAYOUT_CHANNEL_FIRST)
-        return fail(CS_EUNSUPPORTED, "the double-precision path works on the reference (channel-first) layout");
+        return fail(CS_EUNSUPPORTED, "the double / half precision paths work on the reference (channel-first) layout");
     if (pb->N == 0 || pb->C == 0 || pb->P == 0) return CS_NOTHING_TO_DO;
     if (!grid || !offset) return fail(CS_EINVAL, "grid/offset pointer is NULL");
     const long long T = (long long)pb->D * pb->H * pb->W;
@@ -570,13 +571,39 @@ int scalar_setup(const cs_problem* pb, cs::ScalarParams& p, const double* grid, 
     return 0;
 }
 
-int scalar_run(const cs_problem* pb, const cs::ScalarParams& p, int stage, void* stream) {
-    cudaError_t e = (pb->dim == 2) ? cs::launch_scalar<2>(stage, p, (cudaStream_t)stream)
-                                   : cs::launch_scalar<3>(stage, p, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "double-precision stage kernel launch");
+template <typename T>
+int scalar_run(const cs_problem* pb, const cs::ScalarParamsT<T>& p, int stage, void* stream) {
+    cudaError_t e = (pb->dim == 2) ? cs::launch_scalar<2, T>(stage, p, (cudaStream_t)stream)
+                                   : cs::launch_scalar<3, T>(stage, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "double / half precision stage kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
+
+
+// fp16: gInput accumulates in a float workspace (zeroed here) and is rounded to half after the stage kernel
+int half_begin(const cs_problem* pb, const void* gInput, float* workspace, const char* who, void* stream) {
+    if (!gInput) return 0;
+    if (!workspace) return fail(CS_EINVAL, "%s: gInput needs the float workspace (N*C*D*H*W floats)", who);
+    const size_t n = (size_t)pb->N * pb->C * pb->D * pb->H * pb->W;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, n * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fp16 workspace memset");
+    return 0;
+}
+int half_finish(const cs_problem* pb, cs_half* gInput, const float* workspace, void* stream) {
+    if (!gInput) return 0;
+    const long long n = (long long)pb->N * pb->C * pb->D * pb->H * pb->W;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) return 0;
+    cs::cs_f32_to_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(workspace, reinterpret_cast<__half*>(gInput), n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fp16 conversion kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+inline const __half* hp(const cs_half* p) { return reinterpret_cast<const __half*>(p); }
+inline __half* hp(cs_half* p) { return reinterpret_cast<__half*>(p); }
 
 }  // namespace
 
@@ -695,6 +722,63 @@ int cs_backward_backward_backward_f64(const cs_problem* pb, const double* input,
     p.x1 = gOut.ptr; p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
     if (gOutggOut.ptr && gInput) { p.x2 = gOutggOut.ptr; p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
     return scalar_run(pb, p, cs::ST_BBB, stream);
+}
+
+int cs_forward_f16(const cs_problem* pb, const cs_half* input, const cs_half* grid, const float* offset, cs_half* out,
+                   void* stream) {
+    cs::ScalarParamsT<__half> p;
+    if (int rc = scalar_setup<__half>(pb, p, hp(grid), offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!input || !out) return fail(CS_EINVAL, "cs_forward_f16: input/out is NULL");
+    p.V = hp(input); p.y = hp(out);
+    return scalar_run(pb, p, cs::ST_F, stream);
+}
+
+int cs_backward_f16(const cs_problem* pb, cs_stream_f16 gOut, const cs_half* input, const cs_half* grid,
+                    const float* offset, cs_half* gInput, cs_half* gGrid, float* workspace, void* stream) {
+    cs::ScalarParamsT<__half> p;
+    if (int rc = scalar_setup<__half>(pb, p, hp(grid), offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr) return fail(CS_EINVAL, "cs_backward_f16: gOut is NULL");
+    if (gGrid && !input) return fail(CS_EINVAL, "cs_backward_f16: gGrid needs input");
+    if (!gInput && !gGrid) return 0;
+    if (int rc = half_begin(pb, gInput, workspace, "cs_backward_f16", stream)) return rc;
+    p.V = hp(input); p.acc = gInput ? workspace : nullptr; p.ggrid = hp(gGrid);
+    p.x1 = hp(gOut.ptr); p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (int rc = scalar_run(pb, p, cs::ST_B, stream)) return rc;
+    return half_finish(pb, gInput, workspace, stream);
+}
+
+int cs_backward_backward_f16(const cs_problem* pb, const cs_half* gOutInput, const cs_half* gOutGrid,
+                             const cs_half* input, const cs_half* grid, cs_stream_f16 gOut, const float* offset,
+                             cs_half* gInput, cs_half* gGrid, cs_half* ggOut, float* workspace, void* stream) {
+    cs::ScalarParamsT<__half> p;
+    if (int rc = scalar_setup<__half>(pb, p, hp(grid), offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr || !gOutGrid) return fail(CS_EINVAL, "cs_backward_backward_f16: gOut/gOutGrid is NULL");
+    if ((gGrid || ggOut) && !input) return fail(CS_EINVAL, "cs_backward_backward_f16: gGrid/ggOut need input");
+    if (!gInput && !gGrid && !ggOut) return 0;
+    if (int rc = half_begin(pb, gInput, workspace, "cs_backward_backward_f16", stream)) return rc;
+    p.V = hp(input); p.U = hp(gOutInput); p.acc = gInput ? workspace : nullptr; p.ggrid = hp(gGrid); p.y = hp(ggOut);
+    p.gog = hp(gOutGrid);
+    p.x1 = hp(gOut.ptr); p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (int rc = scalar_run(pb, p, cs::ST_BB, stream)) return rc;
+    return half_finish(pb, gInput, workspace, stream);
+}
+
+int cs_backward_backward_backward_f16(const cs_problem* pb, const cs_half* input, const cs_half* grid,
+                                      cs_stream_f16 gOut, const cs_half* gOutGrid, const cs_half* gOutgGrid,
+                                      cs_stream_f16 gOutggOut, const float* offset, cs_half* gInput, cs_half* ggOut,
+                                      float* workspace, void* stream) {
+    cs::ScalarParamsT<__half> p;
+    if (int rc = scalar_setup<__half>(pb, p, hp(grid), offset)) return rc == CS_NOTHING_TO_DO ? 0 : rc;
+    if (!gOut.ptr || !gOutGrid || !gOutgGrid)
+        return fail(CS_EINVAL, "cs_backward_backward_backward_f16: gOut/gOutGrid/gOutgGrid is NULL");
+    if (ggOut && !input) return fail(CS_EINVAL, "cs_backward_backward_backward_f16: ggOut needs input");
+    if (!gInput && !ggOut) return 0;
+    if (int rc = half_begin(pb, gInput, workspace, "cs_backward_backward_backward_f16", stream)) return rc;
+    p.V = hp(input); p.acc = gInput ? workspace : nullptr; p.y = hp(ggOut); p.gog = hp(gOutGrid); p.gogg = hp(gOutgGrid);
+    p.x1 = hp(gOut.ptr); p.x1_sn = gOut.stride_n; p.x1_sc = gOut.stride_c;
+    if (gOutggOut.ptr && gInput) { p.x2 = hp(gOutggOut.ptr); p.x2_sn = gOutggOut.stride_n; p.x2_sc = gOutggOut.stride_c; }
+    if (int rc = scalar_run(pb, p, cs::ST_BBB, stream)) return rc;
+    return half_finish(pb, gInput, workspace, stream);
 }
 
 int cs_jet_forward(const cs_problem* pb, int32_t order, const float* input, const float* coords,

@@ -111,7 +111,7 @@ def _check(t, name, contiguous=True):
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor" % name)
     if t.dtype != torch.float32:
-        raise RuntimeError("%s must be float32 (or float64 together with input: the double-precision path), got %s"
+        raise RuntimeError("%s must be float32 (or float64 / float16 together with input: the scalar paths), got %s"
                            % (name, t.dtype))
     if contiguous and not t.is_contiguous():
         raise RuntimeError("%s must be contiguous" % name)
@@ -290,7 +290,7 @@ def _finish_accumulator(acc, input, layout):
 # ---------------------------------------------------------------------------
 def forward(input, grid, offset, padding_mode, align_corners, kernel, multicell, staged=None):
     """`_cosine_Xd.forward` (cpp2d:47-62): returns out [N,C,*grid.shape[1:-1]]."""
-    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+    if isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16):
         from . import ops_f64
         return ops_f64.forward(input, grid, offset, padding_mode, align_corners, kernel, multicell)
     _check(input, "input")
@@ -312,7 +312,7 @@ def backward(gOut, input, grid, offset, padding_mode, align_corners, input_requi
              multicell, staged=None, want_grid=True):
     """`_cosine_Xd.backward` (cpp2d:64-85): returns (gInput or None, gGrid).
     want_grid=False additionally elides gGrid (returns None for it)."""
-    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+    if isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16):
         from . import ops_f64
         return ops_f64.backward(gOut, input, grid, offset, padding_mode, align_corners, input_requires_grad, kernel,
                                 multicell, want_grid=want_grid)
@@ -349,7 +349,7 @@ def backward_backward(gOutInput, gOutGrid, input, grid, gOut, offset, padding_mo
                       input_requires_grad, kernel, multicell, staged=None, want=(True, True, True)):
     """`_cosine_Xd.backward_backward` (cpp2d:87-106): returns (gInput, gGrid, ggOut).
     gOutInput is read only when input_requires_grad (mod2d:87); `want` elides outputs."""
-    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+    if isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16):
         from . import ops_f64
         return ops_f64.backward_backward(gOutInput, gOutGrid, input, grid, gOut, offset, padding_mode, align_corners,
                                          input_requires_grad, kernel, multicell, want=want)
@@ -401,7 +401,7 @@ def backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, p
     """`_cosine_Xd.backward_backward_backward` (cpp2d:108-127): returns (gInput, ggOut).
     input_requires_grad is accepted and ignored, as in the reference kernel (cu2d:736).
     gOutggOut fuses the `b_input` pass of modules_2d.py:109 into the same kernel."""
-    if isinstance(input, torch.Tensor) and input.dtype == torch.float64:
+    if isinstance(input, torch.Tensor) and input.dtype in (torch.float64, torch.float16):
         from . import ops_f64
         return ops_f64.backward_backward_backward(input, grid, gOut, gOutGrid, gOutgGrid, offset, padding_mode,
                                                   align_corners, input_requires_grad, kernel, multicell, want=want,

@@ -148,6 +148,31 @@ int cs_backward_backward_backward_f64(const cs_problem *pb, const double *input,
                                       cs_stream_f64 gOutggOut, const float *offset, double *gInput,
                                       double *ggOut, void *stream);
 
+/* ---- Half precision --------------------------------------------------------------
+ * The third type of the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF (cu2d:905,948,1009,1076); like the double
+ * instantiation it cannot run in the reference (float offset tensor through TensorInfo<at::Half>, cu2d:914).
+ * Tensors are IEEE binary16 (cs_half = the 16 raw bits), coordinates included, offset stays fp32; every value is
+ * widened to float, the arithmetic is the fp32 formulas, results are rounded to half once.  gInput is accumulated
+ * in `workspace` (N*C*D*H*W floats, device; zeroed by the call; nullable when gInput is NULL) and then rounded
+ * into gInput, which therefore needs no zero-initialisation.  A correctness path; no throughput claim. */
+typedef uint16_t cs_half;
+typedef struct cs_stream_f16 {
+    const cs_half *ptr;
+    int64_t stride_n; /* elements */
+    int64_t stride_c; /* elements */
+} cs_stream_f16;
+int cs_forward_f16(const cs_problem *pb, const cs_half *input, const cs_half *grid, const float *offset,
+                   cs_half *out, void *stream);
+int cs_backward_f16(const cs_problem *pb, cs_stream_f16 gOut, const cs_half *input, const cs_half *grid,
+                    const float *offset, cs_half *gInput, cs_half *gGrid, float *workspace, void *stream);
+int cs_backward_backward_f16(const cs_problem *pb, const cs_half *gOutInput, const cs_half *gOutGrid,
+                             const cs_half *input, const cs_half *grid, cs_stream_f16 gOut, const float *offset,
+                             cs_half *gInput, cs_half *gGrid, cs_half *ggOut, float *workspace, void *stream);
+int cs_backward_backward_backward_f16(const cs_problem *pb, const cs_half *input, const cs_half *grid,
+                                      cs_stream_f16 gOut, const cs_half *gOutGrid, const cs_half *gOutgGrid,
+                                      cs_stream_f16 gOutggOut, const float *offset, cs_half *gInput,
+                                      cs_half *ggOut, float *workspace, void *stream);
+
 /* ---- Fused multi-cell jet operator (not in the reference; SURVEY section 8f ranks 1 + 2) ------------
  * One gather pass replaces the forward, first-backward (gGrid) and double-backward (gGrid) calls of
  * modules_2d.py:22-74 for a point set shared by all N cells (test_2d.py:36-38) and the caller's sum

@@ -153,3 +153,32 @@ def test_one_pass_entry_points_validate_arguments_without_a_gpu():
     assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == -1 and b"NULL" in lib.cs_last_error()
     pb.P = 0
     assert lib.cs_pde_fused_step(ctypes.byref(pb), *args) == 0             # empty problem: nothing to launch
+
+
+def test_scalar_precision_entry_points_validate_arguments_without_a_gpu():
+    """cs_*_f64 / cs_*_f16 reject bad problems and NULL tensors before any CUDA call; the half path insists on its
+    float workspace when gInput is wanted."""
+    from cosinesampler_b200 import _lib
+    lib = _lib.load()
+    pb = _lib.Problem()
+    pb.dim, pb.N, pb.C, pb.D, pb.H, pb.W, pb.P = 2, 2, 3, 1, 8, 8, 16
+    pb.align_corners, pb.multicell = 1, 1
+    pb.field_layout = _lib.LAYOUT_CHANNEL_FIRST
+    one = ctypes.c_void_p(256)                      # a non-NULL pointer that is never dereferenced on these paths
+    null_stream = _lib.Stream3(None, 0, 0)
+    for sfx in ("_f64", "_f16"):
+        fwd = getattr(lib, "cs_forward" + sfx)
+        assert fwd(ctypes.byref(pb), None, one, one, None, None) == -1 and b"NULL" in lib.cs_last_error()
+        assert fwd(ctypes.byref(pb), None, None, None, None, None) == -1
+        pb.field_layout = _lib.LAYOUT_CHANNEL_LAST
+        assert fwd(ctypes.byref(pb), one, one, one, one, None) == -2 and b"channel-first" in lib.cs_last_error()
+        pb.field_layout = _lib.LAYOUT_CHANNEL_FIRST
+        pb.P = 0
+        assert fwd(ctypes.byref(pb), None, None, None, None, None) == 0          # empty problem
+        pb.P = 16
+    assert lib.cs_backward_f64(ctypes.byref(pb), null_stream, one, one, one, one, one, None) == -1
+    assert lib.cs_backward_f16(ctypes.byref(pb), null_stream, one, one, one, one, one, None, None) == -1
+    gs = _lib.Stream3(256, 0, 0)
+    assert lib.cs_backward_f16(ctypes.byref(pb), gs, one, one, one, one, one, None, None) == -1
+    assert b"workspace" in lib.cs_last_error()
+    assert lib.cs_backward_f16(ctypes.byref(pb), gs, one, one, one, None, None, None, None) == 0     # nothing wanted

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn `ncu --page raw --csv` exports of tools/profile_stages.py (two launches per stage variant,
 the second one is kept) into the small summaries under profiles/ that bench.py reads for
-`roofline.traffic`.  Usage: summarize_ncu.py <raw.csv> <out.json> <cfg3|cfg4>"""
+`roofline.traffic`.  Usage: summarize_ncu.py <raw.csv> <out.json> <cfg3|cfg4|onepass_cfg3|...> [points per launch]"""
 import csv
 import json
 import sys
@@ -23,7 +23,7 @@ NOTE = {"cfg3": "cells [4,16,256,256], 2^20 points, cosine multicell",
 SCALE = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
 
-def main(raw, out, cfg):
+def main(raw, out, cfg, points=None):
     rows = list(csv.reader(open(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
 
@@ -52,7 +52,9 @@ def main(raw, out, cfg):
     doc = {"source": "ncu --set full --clock-control none, %s (%s); second launch of each kernel" % (cfg, NOTE[cfg]),
            "kernels": summary}
     if cfg in POINTS:
-        doc["points_per_launch"] = POINTS[cfg]
+        doc["points_per_launch"] = int(points) if points else POINTS[cfg]
+        if points:
+            doc["source"] = doc["source"].replace("2^22 binned points", "%d binned points" % int(points))
     json.dump(doc, open(out, "w"), indent=1)
     for k, v in summary.items():
         print("%-14s %8.1f us  dram %7.1f MB  L2->L1 %7.1f MB  l1tex %4.1f%% req %4.1f%% lts %4.1f%% dram %4.1f%% issue %4.1f%% regs %d"
@@ -61,4 +63,4 @@ def main(raw, out, cfg):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
