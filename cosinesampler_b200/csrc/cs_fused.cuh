@@ -835,10 +835,10 @@ constexpr int FUSED_UNROLL_P1 = CS_FUSED_UNROLL_P1;
 constexpr int FUSED_UNROLL_C = CS_FUSED_UNROLL_C;
 constexpr int FUSED_MAX_CELLS = 32;      // the records of all cells of a tile live in shared memory
 
-// Code size matters here: three inlined phases unrolled over the points of a walker were 8000 SASS
-// instructions (128 KB) and the kernel stalled on instruction fetch.  Gather + head run one point at a time in
-// a real loop (the finished point is rotated into the register tile), phase 1 has one call site, and corners
-// need no validity predicates: ~1500 instructions.
+// Code size matters here: the first version (scalar arithmetic, three inlined phases unrolled over the points of a
+// walker) was 8000 SASS instructions (128 KB) and stalled on instruction fetch.  Phase 1 has one call site, corners
+// need no validity predicates (dump texel), the arithmetic is packed (two hidden units per instruction): 4096
+// instructions with gather + head unrolled over the PPQ points, `no_instruction` stalls 0.15 per issue.
 // NC: number of cells when it is known at compile time (4: the PIXEL configurations; the gather loop over the
 // cells is then fully unrolled and all its loads are in flight together), 0 = run-time p.N.
 template <int DIM, int LSHIFT, int NC>
@@ -928,29 +928,21 @@ cs_pde_fused_kernel(const FusedParams p) {
 
         // acc[jt][t][h] = d loss / d H_jt of point t of this walker, hidden units 4j + 2h, 4j + 2h + 1
         f2 acc[J][PPQ][2];
-#pragma unroll
-        for (int jt = 0; jt < J; ++jt)
-#pragma unroll
-            for (int t = 0; t < PPQ; ++t) { acc[jt][t][0] = zero2; acc[jt][t][1] = zero2; }
 
-        // ---- A + B, one point at a time
-#pragma unroll 1
+        // ---- A + B for the PPQ points of this walker.  The loop is unrolled: d loss / d H of point t lands in its
+        // slot of the register tile directly.  (Round 2's first versions kept it a real loop, with the finished point
+        // rotated into the tile by 80 moves, because the unrolled scalar code -- 8000 instructions -- stalled on
+        // instruction fetch; with packed pairs the unrolled kernel is 4096 instructions and faster than the loop:
+        // 5.84 -> 5.74 ms per 2^25 points, 3D 1.62 -> 1.58 ms per 2^22; unrolling the scatter over the cells or
+        // phase 1 as well still loses, 5.92 / 6.05 ms, profiles/README.md.)
+#pragma unroll
         for (int t = 0; t < PPQ; ++t) {
             const int ri = rec_slot(PPQ * q + t);
             f2 h[J][2];
             fused_gather_point<DIM, LSHIFT, NC>(p, recw, ri, ncells, j, h);
             fused_head_point<DIM, LSHIFT>(p, hl, qp0 + t < p.P, j, h);
-            // the finished point enters the register tile at the top; after PPQ rounds point t sits in slot t
-            // (registers cannot be indexed by t; a warp-uniform switch over the slot measured 3 % slower than
-            // these moves)
 #pragma unroll
-            for (int jt = 0; jt < J; ++jt)
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                    for (int sl = 0; sl + 1 < PPQ; ++sl) acc[jt][sl][hh] = acc[jt][sl + 1][hh];
-                    acc[jt][PPQ - 1][hh] = h[jt][hh];
-                }
+            for (int jt = 0; jt < J; ++jt) { acc[jt][t][0] = h[jt][0]; acc[jt][t][1] = h[jt][1]; }
         }
 
         // ---- C: scatter d loss / d H_jt into gVh (separable adjoint: per corner  Wy u_x +- Wx beta), pre-reduced in

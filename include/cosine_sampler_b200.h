@@ -222,7 +222,7 @@ int cs_pde_head_step(int32_t dim, int32_t C, int64_t P, const float *jets, const
  * by texel (cs_bin_points) the kernel gathers from cache and pre-reduces its scatter in registers. */
 
 /* Counting sort of coords [P, dim] on a tile-major texel key (8x8 texels in 2D, 4x4x4 in 3D) of cell 0,
- * refined by the sub-texel quadrant when the point density allows (>= 4 points per sub-bin).
+ * refined by the sub-texel quadrant when the point density allows (>= 2 points per sub-bin).
  * sorted [P, dim]; perm [P] (nullable): perm[i] = index in coords of sorted point i.  offset [N] device
  * (nullable).  workspace: cs_bin_workspace_bytes() bytes of device scratch.  Order inside a bin is not
  * deterministic.  Uses pb->dim, D/H/W, P, align_corners, multicell, index_mode. */

@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--variants", default="onepass,onepass_noagg,onepass_unbinned,jets")
     ap.add_argument("--once", action="store_true", help="one step per variant, no timing (for ncu)")
+    ap.add_argument("--chunk", type=int, default=0, help="points per chunk of the one-pass step (0: one chunk)")
     args = ap.parse_args()
     dim, shape, kernel, residual = SHAPES[args.workload]
     dev = torch.device("cuda:0")
@@ -81,7 +82,7 @@ def main():
                     return jet.fused_pde_step(cells, coords, head, residual, kernel=kernel, mode="jets")
                 kw = {"onepass": dict(bin=True, aggregate="auto"), "onepass_noagg": dict(bin=True, aggregate="off"),
                       "onepass_unbinned": dict(bin=False, aggregate="off")}[variant]
-                return fused.one_pass_pde_step(cells, coords, head, residual, kernel=kernel, **kw)
+                return fused.one_pass_pde_step(cells, coords, head, residual, kernel=kernel, chunk=args.chunk or None, **kw)
             if args.once:
                 step()
                 torch.cuda.synchronize()
@@ -91,7 +92,7 @@ def main():
             gsum = float(cells.grad.double().abs().sum())
             if ref is None:
                 ref = (loss, gsum)
-            print(json.dumps({"workload": args.workload, "points": P, "variant": variant, "ms_per_step": round(ms, 4),
+            print(json.dumps({"workload": args.workload, "points": P, "variant": variant, "chunk": args.chunk, "ms_per_step": round(ms, 4),
                               "points_per_s": P / (ms * 1e-3), "ms_per_2^20": round(ms * 2 ** 20 / P, 4),
                               "stages_ms": stages, "loss": loss, "grad_abs_sum": gsum}), flush=True)
 
