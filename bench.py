@@ -45,10 +45,10 @@ CHAIN_FIELD_TERMS = {"cfg5": 19, "cfg3": 19, "cfg4": 27}     # grid-shaped tenso
 
 def ncu_traffic_bytes(label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed
-    `ncu --set full` captures of the same shapes (profiles/r3/*_summary.json, else profiles/r2/, r1/; the
+    `ncu --set full` captures of the same shapes (profiles/r2_session2/*_summary.json, else profiles/r2/, r1/; the
     captures drive the same call pattern as this bench: an expanded gOut for the stage kernels, 2^25 (2D) /
     2^22 (3D) binned points per launch for the one-pass kernel).  -> (bytes, points per launch of the capture)"""
-    for rnd, name in (("r3", "ncu_onepass_cfg3_summary.json"), ("r3", "ncu_onepass_cfg4_summary.json"),
+    for rnd, name in (("r2_session2", "ncu_onepass_cfg3_summary.json"), ("r2_session2", "ncu_onepass_cfg4_summary.json"),
                       ("r2", "ncu_stages_cfg3_summary.json"), ("r2", "ncu_stages_cfg4_summary.json"),
                       ("r2", "ncu_onepass_cfg3_summary.json"), ("r2", "ncu_onepass_cfg4_summary.json"),
                       ("r1", "ncu_stages_cfg3_summary.json"), ("r1", "ncu_stages_cfg4_summary.json"),

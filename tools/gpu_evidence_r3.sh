@@ -1,9 +1,9 @@
 #!/bin/bash
 # The GPU evidence pass of round 2's second session (files land under gpurun_out/r3_*; copy the ones to keep into
-# profiles/r3/): ncu --set full of the one-pass kernel at the bench's launch sizes (summaries are written on the
+# profiles/r2_session2/): ncu --set full of the one-pass kernel at the bench's launch sizes (summaries are written on the
 # box too, so that the bench run below reads the instruction counts of THIS build), parity suite, smoke, the default
 # bench line, its launch list, and the measured errors of the one-pass step.  ncu reports are exported and deleted.
-O=gpurun_out; mkdir -p $O profiles/r3
+O=gpurun_out; mkdir -p $O profiles/r2_session2
 for spec in "cfg3 33554432" "cfg4 4194304"; do
   set -- $spec; cfg=$1; pts=$2
   python tools/profile_onepass.py $cfg $pts > $O/plain_$cfg.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:cs_pde_fused -c 2 -o /tmp/op_$cfg python tools/profile_onepass.py $cfg $pts > $O/ncu_onepass_$cfg.log 2>&1
@@ -11,7 +11,7 @@ for spec in "cfg3 33554432" "cfg4 4194304"; do
   ncu -i /tmp/op_$cfg.ncu-rep --page raw --csv > $O/r3_ncu_onepass_${cfg}_raw.csv 2>/dev/null
   ncu -i /tmp/op_$cfg.ncu-rep --page source --csv --print-source cuda,sass > /tmp/src_$cfg.csv 2>/dev/null; python tools/ncu_lines.py /tmp/src_$cfg.csv 70 > $O/r3_ncu_onepass_${cfg}_lines.txt 2>&1
   python tools/summarize_ncu.py $O/r3_ncu_onepass_${cfg}_raw.csv $O/r3_ncu_onepass_${cfg}_summary.json onepass_$cfg $pts
-  cp $O/r3_ncu_onepass_${cfg}_summary.json profiles/r3/ncu_onepass_${cfg}_summary.json
+  cp $O/r3_ncu_onepass_${cfg}_summary.json profiles/r2_session2/ncu_onepass_${cfg}_summary.json
   python tools/ncu_keys.py $O/r3_ncu_onepass_${cfg}_raw.csv | tail -46 > $O/r3_ncu_onepass_${cfg}_keys.txt
 done
 timeout 1500 python -m pytest tests -m gpu -q --maxfail 10 --timeout 600 > $O/r3_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 $O/r3_pytest_gpu.log
