@@ -39,6 +39,12 @@
 
 namespace cs {
 
+// cells per unrolled round of the one-pass kernel's gather (0: all NC cells; experiments)
+#ifndef CS_FUSED_GATHER_UNROLL
+#define CS_FUSED_GATHER_UNROLL 0
+#endif
+constexpr int FUSED_GATHER_UNROLL = CS_FUSED_GATHER_UNROLL;
+
 // ---------------------------------------------------------------------------------------------------------
 // Point binning: counting sort of the coordinates on a tile-major texel key (+ sub-texel quadrant)
 // ---------------------------------------------------------------------------------------------------------
@@ -650,7 +656,7 @@ __device__ __forceinline__ void fused_gather_point(const FusedParams& p, const f
     const f2 zero2 = pk(0.f, 0.f);
 #pragma unroll
     for (int jt = 0; jt < J; ++jt) { h[jt][0] = zero2; h[jt][1] = zero2; }
-#pragma unroll (NC > 0 ? NC : 2)
+#pragma unroll (NC > 0 ? (FUSED_GATHER_UNROLL > 0 ? FUSED_GATHER_UNROLL : NC) : 2)
     for (int n = 0; n < ncells; ++n) {
         const float4* rec = recw + n * REC1;
         const float* vsrc = p.Vh + (long long)n * p.T * K + 4 * j;
