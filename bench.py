@@ -220,7 +220,7 @@ def measure_workload(args, workload, steps, warmup, ctx, with_jets):
     # a chunk holds, the more of them share a texel and the fewer reds leave the SMs); the end-to-end arm cuts
     # the shard into pieces so that the host->device copy of one piece overlaps the pass over the previous one
     fchunk = max(1, nloc)
-    fchunk_e2e = max(2 ** 20, (nloc + 3) // 4)
+    fchunk_e2e = max(2 ** 21, (nloc + 3) // 4)
     reduce_kind = "none (single GPU)"
     fstepper = None
     want_peer = world > 1 and not args.nccl_reduce
