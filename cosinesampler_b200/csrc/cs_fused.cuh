@@ -505,7 +505,8 @@ struct FusedParams {
     int pad, align, kernel, multicell, index_mode;
     int aggregate;            // pre-reduce the scatter over runs of points that share their corners
     long long num_ptiles;     // warp tiles of PTS consecutive points
-    long long tiles_per_warp; // each warp walks a contiguous range of tiles (binned points: cache reuse)
+    long long tiles_per_warp; // tiles per warp (the order in which the warps take them: see the kernel)
+    int group_blocks;         // blocks per SM when the grid is one full wave (else 1): they interleave their tiles
 };
 
 // Phase 1 for one (cell, point).  Record fields (float4 each, [field][point]):
@@ -830,6 +831,9 @@ __device__ __forceinline__ void fused_reduce_head(const FusedParams& p, HeadLane
 // Unrolling over the cells pays for the gather only (NC = 4: 6.68 -> 6.14 ms per 2^25 points, its loads are in
 // flight together).  Unrolling phase 1 and the scatter by 2 / 4 cells grows the code and LOSES: 6.34 / 7.30 ms
 // (profiles/README.md): the kernel lives at the edge of the instruction cache.
+#ifndef CS_FUSED_INTERLEAVE
+#define CS_FUSED_INTERLEAVE -1        // -1: 2 in 2D, 1 in 3D (see the kernel)
+#endif
 #ifndef CS_FUSED_UNROLL_P1
 #define CS_FUSED_UNROLL_P1 1
 #endif
@@ -875,9 +879,30 @@ cs_pde_fused_kernel(const FusedParams p) {
     init_head_lane(hl, p, j);
     const f2 zero2 = pk(0.f, 0.f);
 
-    const long long gw = (long long)blockIdx.x * wpb + warp;
-    const long long tile_begin = gw * p.tiles_per_warp;
-    long long tile_end = tile_begin + p.tiles_per_warp;
+    // Tile order.  Binned points: neighbouring tiles touch the same texels, so the warps that share an L1 should work
+    // on neighbouring tiles at the same time.  IL = 1: a block owns a contiguous range and its warps take the tiles
+    // round-robin.  IL = 2: the `group_blocks` blocks that the hardware places on one SM (blocks b, b + groups,
+    // b + 2 groups ... of a grid of groups x group_blocks blocks launched in one wave) share one range and
+    // interleave all their warps.  IL = 0: every warp walks its own contiguous range (round 2's first version).
+    // Measured per 2^25 / 2^22 points: 2D 5.72 (0) / 5.66 (1) / 5.54 ms (2); 3D 1.57 / 1.53 / 1.57 ms -- in 3D a
+    // warp's own consecutive tiles (one texel each) reuse more than 12 warps side by side.
+    constexpr int IL = CS_FUSED_INTERLEAVE >= 0 ? CS_FUSED_INTERLEAVE : (DIM == 2 ? 2 : 1);
+    long long tile_step, tile_begin, tile_end;
+    if (IL == 2) {
+        const int groups = (int)gridDim.x / p.group_blocks;
+        const int grp = (int)blockIdx.x % groups, member = (int)blockIdx.x / groups;
+        tile_step = (long long)wpb * p.group_blocks;
+        tile_begin = (long long)grp * tile_step * p.tiles_per_warp + member * wpb + warp;
+        tile_end = (long long)(grp + 1) * tile_step * p.tiles_per_warp;
+    } else if (IL == 1) {
+        tile_step = wpb;
+        tile_begin = (long long)blockIdx.x * wpb * p.tiles_per_warp + warp;
+        tile_end = (long long)(blockIdx.x + 1) * wpb * p.tiles_per_warp;
+    } else {
+        tile_step = 1;
+        tile_begin = ((long long)blockIdx.x * wpb + warp) * p.tiles_per_warp;
+        tile_end = tile_begin + p.tiles_per_warp;
+    }
     if (tile_end > p.num_ptiles) tile_end = p.num_ptiles;
 
     // phase 1 runs one (cell, point) per lane: lane -> point (u * 32 + lane) % PTS; when a tile has fewer than 32
@@ -909,9 +934,9 @@ cs_pde_fused_kernel(const FusedParams p) {
     if (tile_begin < tile_end) load_coords(gcur, icur, tile_begin);
 
 #pragma unroll 1
-    for (long long tile = tile_begin; tile < tile_end; ++tile) {
-        const bool have_next = tile + 1 < tile_end;
-        if (have_next) load_coords(gnext, inext, tile + 1);
+    for (long long tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const bool have_next = tile + tile_step < tile_end;
+        if (have_next) load_coords(gnext, inext, tile + tile_step);
         const long long qp0 = tile * PTS + (long long)q * PPQ;      // first point of this walker
 
         // ---- phase 1: records of every cell for the PTS points of this tile, one point per lane
@@ -1088,6 +1113,7 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     if (blocks > need) blocks = need;
     if (blocks < 1) return cudaSuccess;
     p.tiles_per_warp = (p.num_ptiles + blocks * wpb - 1) / (blocks * wpb);
+    p.group_blocks = (blocks == (long long)sms * occ) ? occ : 1;
     kern<<<(unsigned)blocks, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
