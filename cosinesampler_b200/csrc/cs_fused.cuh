@@ -826,13 +826,13 @@ __device__ __forceinline__ void fused_reduce_head(const FusedParams& p, HeadLane
 }
 
 #ifndef CS_FUSED_BLOCKS
-#define CS_FUSED_BLOCKS 3
+#define CS_FUSED_BLOCKS 1
 #endif
 // Unrolling over the cells pays for the gather only (NC = 4: 6.68 -> 6.14 ms per 2^25 points, its loads are in
 // flight together).  Unrolling phase 1 and the scatter by 2 / 4 cells grows the code and LOSES: 6.34 / 7.30 ms
 // (profiles/README.md): the kernel lives at the edge of the instruction cache.
 #ifndef CS_FUSED_INTERLEAVE
-#define CS_FUSED_INTERLEAVE -1        // -1: 2 in 2D, 1 in 3D (see the kernel)
+#define CS_FUSED_INTERLEAVE -1        // -1: the default order (see the kernel)
 #endif
 #ifndef CS_FUSED_UNROLL_P1
 #define CS_FUSED_UNROLL_P1 1
@@ -840,7 +840,12 @@ __device__ __forceinline__ void fused_reduce_head(const FusedParams& p, HeadLane
 #ifndef CS_FUSED_UNROLL_C
 #define CS_FUSED_UNROLL_C 1
 #endif
-constexpr int FUSED_THREADS = 128;
+// ONE block of 12 warps per SM (168 registers): the warps of a block are on one SM by construction, which is what the
+// interleaved tile order needs; 3 blocks of 4 warps relied on the hardware's block placement and were 4 % slower
+#ifndef CS_FUSED_THREADS
+#define CS_FUSED_THREADS 384
+#endif
+constexpr int FUSED_THREADS = CS_FUSED_THREADS;
 constexpr int FUSED_UNROLL_P1 = CS_FUSED_UNROLL_P1;
 constexpr int FUSED_UNROLL_C = CS_FUSED_UNROLL_C;
 constexpr int FUSED_MAX_CELLS = 32;      // the records of all cells of a tile live in shared memory
@@ -880,13 +885,13 @@ cs_pde_fused_kernel(const FusedParams p) {
     const f2 zero2 = pk(0.f, 0.f);
 
     // Tile order.  Binned points: neighbouring tiles touch the same texels, so the warps that share an L1 should work
-    // on neighbouring tiles at the same time.  IL = 1: a block owns a contiguous range and its warps take the tiles
-    // round-robin.  IL = 2: the `group_blocks` blocks that the hardware places on one SM (blocks b, b + groups,
-    // b + 2 groups ... of a grid of groups x group_blocks blocks launched in one wave) share one range and
-    // interleave all their warps.  IL = 0: every warp walks its own contiguous range (round 2's first version).
-    // Measured per 2^25 / 2^22 points: 2D 5.72 (0) / 5.66 (1) / 5.54 ms (2); 3D 1.57 / 1.53 / 1.57 ms -- in 3D a
-    // warp's own consecutive tiles (one texel each) reuse more than 12 warps side by side.
-    constexpr int IL = CS_FUSED_INTERLEAVE >= 0 ? CS_FUSED_INTERLEAVE : (DIM == 2 ? 2 : 1);
+    // on neighbouring tiles at the same time.  IL = 1 (default): a block owns a contiguous range and its warps take
+    // the tiles round-robin.  IL = 2: the `group_blocks` blocks that the hardware places on one SM (blocks b,
+    // b + groups, ... of a grid launched in one wave) share one range and interleave all their warps.  IL = 0: every
+    // warp walks its own contiguous range (round 2's first version).  Measured per 2^25 (2D) / 2^22 (3D) points with
+    // 3 blocks of 4 warps per SM: 5.72 / 1.57 ms (0), 5.66 / 1.53 (1), 5.54 / 1.57 (2); with one block of 12 warps and
+    // IL = 1: 5.34 / 1.52 ms.
+    constexpr int IL = CS_FUSED_INTERLEAVE >= 0 ? CS_FUSED_INTERLEAVE : 1;
     long long tile_step, tile_begin, tile_end;
     if (IL == 2) {
         const int groups = (int)gridDim.x / p.group_blocks;
@@ -1090,7 +1095,7 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     auto kern = (p.N == 4) ? cs_pde_fused_kernel<DIM, LSHIFT, 4> : cs_pde_fused_kernel<DIM, LSHIFT, 0>;
     const size_t per_warp = (size_t)p.N * REC1 * sizeof(float4);
     int wpb = FUSED_THREADS / 32;
-    while (wpb > 1 && wpb * per_warp > 72 * 1024) wpb >>= 1;      // three blocks per SM where the records allow
+    while (wpb > 1 && wpb * per_warp > (216 / CS_FUSED_BLOCKS) * 1024) wpb >>= 1;   // CS_FUSED_BLOCKS blocks per SM where the records allow
     const int threads = wpb * 32;
     size_t smem = wpb * per_warp;
     const size_t red_bytes = (size_t)wpb * (2 * K + 2) * sizeof(float);
