@@ -1095,24 +1095,26 @@ cudaError_t launch_fused_one(FusedParams& p, cudaStream_t stream) {
     auto kern = (p.N == 4) ? cs_pde_fused_kernel<DIM, LSHIFT, 4> : cs_pde_fused_kernel<DIM, LSHIFT, 0>;
     const size_t per_warp = (size_t)p.N * REC1 * sizeof(float4);
     int wpb = FUSED_THREADS / 32;
-    while (wpb > 1 && wpb * per_warp > (216 / CS_FUSED_BLOCKS) * 1024) wpb >>= 1;   // CS_FUSED_BLOCKS blocks per SM where the records allow
+    while (wpb > 1 && wpb * per_warp > (216 / CS_FUSED_BLOCKS) * 1024) wpb >>= 1;   // the records of a block must fit
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    p.num_ptiles = (p.P + PTS - 1) / PTS;
+    // few points: smaller blocks, so that the tiles still spread over all SMs
+    if (p.num_ptiles < (long long)sms * wpb) wpb = (int)((p.num_ptiles + sms - 1) / sms);
+    if (wpb < 1) wpb = 1;
     const int threads = wpb * 32;
     size_t smem = wpb * per_warp;
     const size_t red_bytes = (size_t)wpb * (2 * K + 2) * sizeof(float);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    p.num_ptiles = (p.P + PTS - 1) / PTS;
     long long blocks = (long long)sms * occ;
     const long long need = (p.num_ptiles + wpb - 1) / wpb;
     if (blocks > need) blocks = need;
