@@ -92,3 +92,31 @@ def test_shard_range_partitions_points():
                 assert e0 == s1
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_record_slots_of_the_one_pass_kernel_are_bank_conflict_free():
+    """cs_fused.cuh `rec_slot(i) = i + (i >> 3)`: the L lanes of a walker read the same 16-byte record and the walkers
+    of a warp read records PPQ points apart.  Model of an LDS.128 / STS.128: identical addresses are merged over
+    the warp, the rest is served in wavefronts of one address per 16-byte bank group (8 groups).  With slot = point
+    the reads of the K = 16 kernel need 4 wavefronts, with the spare slot per 8 points the minimum for every hidden
+    width, and the one-point-per-lane writes of phase 1 stay at their minimum too."""
+    from collections import Counter
+
+    def wavefronts(slots):
+        return max(Counter(s % 8 for s in set(slots)).values())
+
+    for dim, ppq in ((2, 4), (3, 2)):
+        for lshift in range(5):
+            nw = 32 >> lshift
+            pts = ppq * nw
+            ideal_read = max(1, nw * 16 // 128)
+            for name, slot in (("plain", lambda i: i), ("padded", lambda i: i + (i >> 3))):
+                reads = [wavefronts([slot(ppq * (lane >> lshift) + t) for lane in range(32)]) for t in range(ppq)]
+                lanes_used = min(32, pts * max(1, 32 // pts))
+                writes = [wavefronts([slot((u * 32 + lane) % pts) for lane in range(lanes_used)])
+                          for u in range((pts + 31) // 32)]
+                if name == "padded":
+                    assert all(r == ideal_read for r in reads), (dim, lshift, reads)
+                    assert all(w <= 4 for w in writes)
+                elif dim == 2 and lshift == 2:
+                    assert reads == [4, 4, 4, 4]                # what ncu showed: 40 % of the wavefronts were conflicts
